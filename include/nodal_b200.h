@@ -1,0 +1,181 @@
+/*
+ * nodal_b200 -- C ABI of the B200-native MNA hot path (libnodal_b200.so).
+ *
+ * The reference (EnricoMiccoli/nodal) is pure Python and has no FFI; its de-facto
+ * boundary for this path is the Python object surface (Circuit.build_model,
+ * nodal/nodal.py:338-398; Circuit.solve, nodal/nodal.py:313-336; the write_*
+ * stamp functions, nodal/models.py:13-214).  Each entry point below names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C symbols, plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer supplied (and owned) by the caller unless
+ *     its name ends in _h (host).  Nothing passed in is freed by the library.
+ *   - `stream` is a cudaStream_t passed as void*; calls that return only a status
+ *     are asynchronous on that stream, calls that fill host scalars synchronise it.
+ *   - return value: NODAL_OK, or one of the codes below; a message for the last
+ *     error of the calling thread is available from nodal_last_error().
+ *   - a nodal_ctx owns scratch workspaces for one device; it is not thread safe:
+ *     use one ctx per host thread / stream.
+ */
+#ifndef NODAL_B200_H
+#define NODAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NODAL_ABI_VERSION 1
+
+enum {
+    NODAL_OK = 0,
+    NODAL_SINGULAR = 1,      /* zero pivot in LU; *info_h = 1-based pivot index            */
+    NODAL_NOT_CONVERGED = 2, /* Krylov solver hit maxit; iters / relres are still filled  */
+    NODAL_BREAKDOWN = 3,     /* Krylov breakdown (p.Ap <= 0 in CG, zero Arnoldi vector)   */
+    NODAL_CUDA_ERROR = 4,    /* CUDA / NCCL failure, see nodal_last_error()               */
+    NODAL_BAD_ARG = -1
+};
+
+/* component type codes of the struct-of-arrays table (nodal/constants.py:15-18) */
+enum { NODAL_T_R = 0, NODAL_T_A = 1, NODAL_T_E = 2, NODAL_T_VCVS = 3, NODAL_T_VCCS = 4,
+       NODAL_T_CCVS = 5, NODAL_T_CCCS = 6 };
+#define NODAL_GROUND (-1) /* lead / control index of the ground node */
+#define NODAL_UNUSED (-2)
+
+typedef struct nodal_ctx nodal_ctx;
+
+int nodal_abi_version(void);
+const char* nodal_last_error(void);
+int nodal_ctx_create(int device, nodal_ctx** out);
+int nodal_ctx_destroy(nodal_ctx* ctx);
+/* bytes of device scratch currently held by the ctx */
+int64_t nodal_ctx_workspace_bytes(nodal_ctx* ctx);
+
+/* ---------------------------------------------------------------- stamping
+ * Replaces the loop of Circuit.build_model (nodal/nodal.py:357-390) and the
+ * write_R/A/E/VCVS/CCVS/CCCS stamp functions (nodal/models.py:13-214).
+ *
+ * Reads the component table (one row per component, stamping order) and emits
+ * `stride` keyed triples per component into keys/vals (capacity stride*ncomp):
+ *   key = (row << colbits) | col, val = contribution.  Right-hand-side
+ *   contributions use col == n.  Unused slots get row == n (sorts last).
+ * stride must be >= the largest number of entries any present type emits
+ * (R 4, A 2, E 5, VCVS/VCCS/CCVS 6, CCCS 5); colbits = bits needed for n.
+ * Within-component '=' / '+=' ordering of the reference is resolved here, so
+ * the later reduction is a pure in-order sum.
+ */
+int nodal_stamp_coo(nodal_ctx* ctx, int64_t ncomp,
+                    const uint8_t* type, const double* value,
+                    const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d,
+                    const int32_t* drv, const int32_t* branch,
+                    int32_t kcl, int32_t n, int32_t stride, int32_t colbits,
+                    uint64_t* keys, double* vals, void* stream);
+
+/* ---------------------------------------------------------------- CSR build
+ * Replaces dok_matrix accumulation + G.tocsr() (nodal/nodal.py:349-351,396-397)
+ * and the in-place sum_duplicates() spsolve performs (canonical sorted columns).
+ *
+ * Phase 1: stable LSD radix sort of (keys, vals) [both are clobbered], in-order
+ * segmented sum of duplicates (reproduces the reference's summation order bit for
+ * bit), removal of exact zeros (DOK semantics), split of the col == n entries
+ * into rhs[n] (rhs is fully overwritten).  Returns nnz in *nnz_h (synchronises).
+ * Phase 2: copies the result into caller buffers indptr[n+1], indices[nnz],
+ * data[nnz].
+ */
+int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
+                    uint64_t* keys, double* vals, double* rhs,
+                    int64_t* nnz_h, void* stream);
+int nodal_csr_fetch(nodal_ctx* ctx, int32_t n, int64_t nnz,
+                    int32_t* indptr, int32_t* indices, double* data, void* stream);
+
+/* CSR -> dense row-major n x n (dense mode of build_model, nodal/nodal.py:352-353).
+ * G is fully overwritten. */
+int nodal_csr_to_dense(nodal_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                       const double* data, double* G, void* stream);
+/* Dense scatter-add of the keyed triples with warp-aggregated atomics (fast,
+ * summation order not reproducible).  G (n x n) and rhs (n) are overwritten. */
+int nodal_coo_to_dense_atomic(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
+                              const uint64_t* keys, const double* vals, double* G, double* rhs,
+                              void* stream);
+
+/* ---------------------------------------------------------------- sparse kernels */
+/* y = A x (CSR, f64 values, i32 indices). */
+int nodal_spmv(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+               const int32_t* indices, const double* data, const double* x, double* y,
+               void* stream);
+
+/* Solver-private sliced-ELL copy of a CSR matrix (slice height 32).  The handle
+ * is owned by the ctx-independent library heap; free with nodal_sell_destroy. */
+typedef struct nodal_sell nodal_sell;
+int nodal_sell_create(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+                      const int32_t* indices, const double* data, nodal_sell** out, void* stream);
+int nodal_sell_destroy(nodal_sell* m);
+int64_t nodal_sell_padded_nnz(const nodal_sell* m);
+int nodal_sell_spmv(nodal_ctx* ctx, const nodal_sell* m, const double* x, double* y, void* stream);
+
+/* Jacobi-preconditioned conjugate gradients, FP64.  Replaces
+ * scipy.sparse.linalg.spsolve at nodal/nodal.py:325 for SPD (R / A only) netlists.
+ * x holds the initial guess on entry and the solution on exit.  Converged when
+ * ||b - A x||_2 <= rtol * ||b||_2 (checked on the true residual at the end).
+ * stats_h (optional, 8 doubles): [0] iterations, [1] relres (true), [2] restarts,
+ * [3] solve ms (device), [4] setup ms, [5] format (0 csr, 1 sell), [6] padded nnz, [7] -. */
+int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+              const int32_t* indices, const double* data, const double* rhs, double* x,
+              double rtol, int32_t maxit, int32_t flags,
+              int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
+#define NODAL_PCG_FORCE_CSR 1   /* do not build the sliced-ELL copy          */
+#define NODAL_PCG_NO_GRAPH 2    /* launch kernels directly (debug / profile) */
+
+/* Restarted GMRES(m) with diagonal (zero-safe) right preconditioning, FP64.
+ * Replaces spsolve at nodal/nodal.py:325 when controlled / voltage sources make
+ * G non-symmetric. */
+int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+                const int32_t* indices, const double* data, const double* rhs, double* x,
+                double rtol, int32_t restart, int32_t maxit,
+                int32_t* iters_h, double* relres_h, void* stream);
+
+/* ---------------------------------------------------------------- dense kernels
+ * Blocked FP64 LU with partial pivoting + triangular solves.  Replaces
+ * numpy.linalg.solve (LAPACK dgesv) at nodal/nodal.py:327.  G (n x n row-major)
+ * is overwritten by its factors; x receives the solution (rhs untouched).
+ * NODAL_SINGULAR with *info_h = k (1-based) when the k-th pivot is exactly zero,
+ * matching dgesv's info > 0 -> numpy LinAlgError. */
+int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double* rhs, double* x,
+                   int32_t* info_h, void* stream);
+
+/* Batched small systems sharing one topology: for copy s in [0, batch) stamp the
+ * table with values[s*ncomp .. +ncomp) and solve the n x n system (n <= 32) with
+ * partially pivoted LU in one thread.  x is batch x n row-major; info[s] = 0 or
+ * the 1-based index of a zero pivot.  Replaces a loop of Netlist+Circuit+solve
+ * over parameter sweeps (config C4). */
+int nodal_lu_batched(nodal_ctx* ctx, int64_t batch, int32_t ncomp,
+                     const uint8_t* type, const int32_t* a, const int32_t* b,
+                     const int32_t* c, const int32_t* d, const int32_t* drv, const int32_t* branch,
+                     int32_t kcl, int32_t n, const double* values, double* x, int32_t* info,
+                     void* stream);
+
+/* ---------------------------------------------------------------- multi-GPU
+ * Row-partitioned PCG: rank k owns rows [row_begin, row_end) of the global
+ * system as a local CSR whose column indices are GLOBAL.  Halo exchange of the
+ * off-rank x entries + scalar all-reduces run over NCCL (dlopen'ed libnccl.so.2).
+ * The 128-byte unique id is created on rank 0 and distributed by the caller
+ * (torch.distributed broadcast). */
+typedef struct nodal_dist nodal_dist;
+int nodal_dist_unique_id(uint8_t id_h[128]);
+int nodal_dist_create(nodal_ctx* ctx, const uint8_t id_h[128], int32_t rank, int32_t nranks,
+                      nodal_dist** out);
+int nodal_dist_destroy(nodal_dist* d);
+int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global,
+                   int32_t row_begin, int32_t row_end,
+                   const int32_t* indptr, const int32_t* indices, const double* data,
+                   const double* rhs_local, double* x_local,
+                   double rtol, int32_t maxit,
+                   int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NODAL_B200_H */

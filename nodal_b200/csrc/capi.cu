@@ -1,0 +1,80 @@
+// Context, error reporting and scratch arena of libnodal_b200.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void nodal_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int nodal_abi_version(void) { return NODAL_ABI_VERSION; }
+extern "C" const char* nodal_last_error(void) { return g_err; }
+
+extern "C" int nodal_ctx_create(int device, nodal_ctx** out) {
+    if (!out) return NODAL_BAD_ARG;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) {
+        nodal_set_error("nodal_ctx_create: device %d out of range (%d visible)", device, count);
+        return NODAL_BAD_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        nodal_set_error("nodal_b200 needs an sm_100a device, found sm_%d%d", prop.major, prop.minor);
+        return NODAL_CUDA_ERROR;
+    }
+    nodal_ctx* ctx = new nodal_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaMallocHost(&ctx->pinned, 4096));
+    *out = ctx;
+    return NODAL_OK;
+}
+
+extern "C" int nodal_ctx_destroy(nodal_ctx* ctx) {
+    if (!ctx) return NODAL_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+    return NODAL_OK;
+}
+
+extern "C" int64_t nodal_ctx_workspace_bytes(nodal_ctx* ctx) {
+    return ctx ? (int64_t)ctx->arena_bytes : 0;
+}
+
+int ctx_reserve(nodal_ctx* ctx, size_t bytes) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    bytes = align_up(bytes + 4096, 1 << 20);
+    if (bytes > ctx->arena_bytes) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (ctx->arena) CUDA_TRY(cudaFree(ctx->arena));
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->arena, bytes));
+        ctx->arena_bytes = bytes;
+    }
+    ctx->arena_used = 0;
+    ctx->generation++;
+    return NODAL_OK;
+}
+
+void* ctx_carve(nodal_ctx* ctx, size_t bytes) {
+    size_t off = align_up(ctx->arena_used, 256);
+    if (off + bytes > ctx->arena_bytes) {
+        nodal_set_error("internal: scratch arena overflow (%zu + %zu > %zu)", off, bytes,
+                        ctx->arena_bytes);
+        return nullptr;
+    }
+    ctx->arena_used = off + bytes;
+    return ctx->arena + off;
+}

@@ -1,0 +1,246 @@
+"""Device-side plumbing: torch tensors as buffers, ctypes calls into libnodal_b200.so.
+
+torch is used only to own device memory, streams and (in dist.py) the process
+group; every kernel that runs here is one of ours.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from . import constants as K
+from .table import ComponentTable
+
+_STRIDE_OF_TYPE = {K.T_R: 4, K.T_A: 2, K.T_E: 5, K.T_VCVS: 6, K.T_VCCS: 6, K.T_CCVS: 6, K.T_CCCS: 5}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def coo_stride(table: ComponentTable) -> int:
+    """Slots per component the stamp kernel must reserve (see include/nodal_b200.h)."""
+    present = np.unique(table.type)
+    need = max((_STRIDE_OF_TYPE[int(t)] for t in present), default=2)
+    return 2 if need <= 2 else 4 if need <= 4 else need
+
+
+def colbits_for(n: int) -> int:
+    return max(1, int(n).bit_length())
+
+
+class DeviceCSR:
+    """CSR matrix + right-hand side resident in HBM (int32 indices, f64 data)."""
+
+    def __init__(self, n, indptr, indices, data):
+        self.n = int(n)
+        self.indptr, self.indices, self.data = indptr, indices, data
+
+    @property
+    def nnz(self):
+        return int(self.data.numel())
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def tocsr(self):
+        """Host scipy.sparse.csr_matrix copy (container only -- no arithmetic)."""
+        import scipy.sparse as sps
+        return sps.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
+                               self.indptr.cpu().numpy()), shape=self.shape)
+
+    def toarray(self):
+        return self.tocsr().toarray()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.toarray()
+        return a if dtype is None else a.astype(dtype)
+
+
+class Device:
+    """One CUDA device + one library context.  Not thread safe (one per thread)."""
+
+    _instances = {}
+    _lock = threading.Lock()
+
+    @classmethod
+    def get(cls, index=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.NodalLibraryError(
+                "nodal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if index is None:
+            index = torch.cuda.current_device()
+        key = (threading.get_ident(), int(index))
+        with cls._lock:
+            if key not in cls._instances:
+                cls._instances[key] = cls(int(index))
+            return cls._instances[key]
+
+    def __init__(self, index):
+        self.torch = _torch()
+        self.index = index
+        self.dev = self.torch.device("cuda", index)
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.nodal_ctx_create(index, C.byref(h)), "nodal_ctx_create")
+        self.ctx = h
+        self.launches = 0   # kernels-of-ours launch counter is kept by the callers' estimates
+
+    # ------------------------------------------------------------ helpers
+    def stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def empty(self, n, dtype):
+        return self.torch.empty(int(n), dtype=dtype, device=self.dev)
+
+    def zeros(self, n, dtype):
+        return self.torch.zeros(int(n), dtype=dtype, device=self.dev)
+
+    def to_device(self, arr, pin=False):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        if pin:
+            t = t.pin_memory()
+        return t.to(self.dev, non_blocking=pin)
+
+    @staticmethod
+    def ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    def upload_table(self, table: ComponentTable, pin=False):
+        return {name: self.to_device(getattr(table, name), pin=pin)
+                for name in ("type", "value", "a", "b", "c", "d", "drv", "branch")}
+
+    # ------------------------------------------------------------ stamping
+    def stamp_coo(self, dtab, ncomp, kcl, n, stride):
+        torch = self.torch
+        cb = colbits_for(n)
+        keys = self.empty(max(1, stride * ncomp), torch.int64)
+        vals = self.empty(max(1, stride * ncomp), torch.float64)
+        p = self.ptr
+        _lib.check(self.lib.nodal_stamp_coo(
+            self.ctx, ncomp, p(dtab["type"]), p(dtab["value"]), p(dtab["a"]), p(dtab["b"]),
+            p(dtab["c"]), p(dtab["d"]), p(dtab["drv"]), p(dtab["branch"]),
+            kcl, n, stride, cb, p(keys), p(vals), self.stream()), "nodal_stamp_coo")
+        return keys, vals, cb
+
+    def assemble_csr(self, table: ComponentTable, dtab=None):
+        """Stamp + CSR build.  Returns (DeviceCSR, rhs tensor)."""
+        torch = self.torch
+        n, ncomp = table.n, len(table)
+        stride = coo_stride(table)
+        if dtab is None:
+            dtab = self.upload_table(table)
+        keys, vals, cb = self.stamp_coo(dtab, ncomp, table.kcl, n, stride)
+        rhs = self.empty(max(1, n), torch.float64)[:n]
+        nnz = C.c_int64(0)
+        p = self.ptr
+        _lib.check(self.lib.nodal_csr_build(self.ctx, n, stride * ncomp, cb, p(keys), p(vals),
+                                            p(rhs), C.byref(nnz), self.stream()), "nodal_csr_build")
+        nnz = nnz.value
+        indptr = self.empty(n + 1, torch.int32)
+        indices = self.empty(max(1, nnz), torch.int32)[:nnz]
+        data = self.empty(max(1, nnz), torch.float64)[:nnz]
+        _lib.check(self.lib.nodal_csr_fetch(self.ctx, n, nnz, p(indptr), p(indices), p(data),
+                                            self.stream()), "nodal_csr_fetch")
+        # keys / vals may back the pending result until fetch has run on the stream
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        del keys, vals
+        return DeviceCSR(n, indptr, indices, data), rhs
+
+    def csr_to_dense(self, csr: DeviceCSR):
+        n = csr.n
+        G = self.empty(max(1, n * n), self.torch.float64)[: n * n].view(n, n)
+        p = self.ptr
+        _lib.check(self.lib.nodal_csr_to_dense(self.ctx, n, p(csr.indptr), p(csr.indices),
+                                               p(csr.data), p(G), self.stream()), "nodal_csr_to_dense")
+        return G
+
+    def assemble_dense(self, table: ComponentTable, atomic=False):
+        """Dense n x n G and rhs.  atomic=False: deterministic (sorted, in-order sums, bit-exact
+        with the reference); atomic=True: warp-aggregated atomic scatter-add."""
+        if not atomic:
+            csr, rhs = self.assemble_csr(table)
+            return self.csr_to_dense(csr), rhs
+        torch = self.torch
+        n, ncomp = table.n, len(table)
+        stride = coo_stride(table)
+        dtab = self.upload_table(table)
+        keys, vals, cb = self.stamp_coo(dtab, ncomp, table.kcl, n, stride)
+        G = self.empty(max(1, n * n), torch.float64)[: n * n].view(n, n)
+        rhs = self.empty(max(1, n), torch.float64)[:n]
+        p = self.ptr
+        _lib.check(self.lib.nodal_coo_to_dense_atomic(self.ctx, n, stride * ncomp, cb, p(keys),
+                                                      p(vals), p(G), p(rhs), self.stream()),
+                   "nodal_coo_to_dense_atomic")
+        return G, rhs
+
+    # ------------------------------------------------------------ sparse solves
+    def spmv(self, csr: DeviceCSR, x):
+        y = self.empty(max(1, csr.n), self.torch.float64)[: csr.n]
+        p = self.ptr
+        _lib.check(self.lib.nodal_spmv(self.ctx, csr.n, csr.nnz, p(csr.indptr), p(csr.indices),
+                                       p(csr.data), p(x), p(y), self.stream()), "nodal_spmv")
+        return y
+
+    def pcg(self, csr: DeviceCSR, rhs, rtol=1e-10, maxit=None, flags=0, x0=None):
+        n = csr.n
+        x = self.zeros(max(2, n), self.torch.float64)[:n] if x0 is None else x0.clone()
+        if maxit is None:
+            maxit = max(5000, 40 * int(np.sqrt(max(n, 1))))
+        iters, relres = C.c_int32(0), C.c_double(0.0)
+        stats = (C.c_double * 8)()
+        p = self.ptr
+        st = self.lib.nodal_pcg(self.ctx, n, csr.nnz, p(csr.indptr), p(csr.indices), p(csr.data),
+                                p(rhs), p(x), rtol, maxit, flags, C.byref(iters), C.byref(relres),
+                                stats, self.stream())
+        _lib.check(st, "nodal_pcg", allowed=(_lib.OK, _lib.NOT_CONVERGED, _lib.BREAKDOWN))
+        info = dict(solver="pcg", status=st, iterations=iters.value, relres=relres.value,
+                    restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4],
+                    format="sell32" if stats[5] else "csr", stored_nnz=int(stats[6]),
+                    spmv_grid=int(stats[7]))
+        return x, info
+
+    def gmres(self, csr: DeviceCSR, rhs, rtol=1e-12, restart=60, maxit=20000):
+        n = csr.n
+        x = self.zeros(max(2, n), self.torch.float64)[:n]
+        iters, relres = C.c_int32(0), C.c_double(0.0)
+        p = self.ptr
+        st = self.lib.nodal_gmres(self.ctx, n, csr.nnz, p(csr.indptr), p(csr.indices), p(csr.data),
+                                  p(rhs), p(x), rtol, restart, maxit, C.byref(iters),
+                                  C.byref(relres), self.stream())
+        _lib.check(st, "nodal_gmres", allowed=(_lib.OK, _lib.NOT_CONVERGED, _lib.BREAKDOWN))
+        return x, dict(solver="gmres", status=st, iterations=iters.value, relres=relres.value)
+
+    # ------------------------------------------------------------ dense solves
+    def lu_solve(self, G, rhs):
+        """Solves G x = rhs; G (n x n, row-major) is overwritten by its LU factors."""
+        n = int(G.shape[0])
+        x = self.empty(max(1, n), self.torch.float64)[:n]
+        info = C.c_int32(0)
+        p = self.ptr
+        st = self.lib.nodal_lu_solve(self.ctx, n, p(G), p(rhs), p(x), C.byref(info), self.stream())
+        _lib.check(st, "nodal_lu_solve", allowed=(_lib.OK, _lib.SINGULAR))
+        return x, dict(solver="lu", status=st, info=info.value)
+
+    def lu_batched(self, table: ComponentTable, values):
+        """values: (batch, ncomp) device tensor.  Returns x (batch, n), info (batch,)."""
+        torch = self.torch
+        batch, ncomp = int(values.shape[0]), int(values.shape[1])
+        if ncomp != len(table):
+            raise ValueError("values must have one column per component of the topology")
+        n = table.n
+        dtab = self.upload_table(table)
+        x = self.empty(max(1, batch * n), torch.float64)[: batch * n].view(batch, n)
+        info = self.empty(max(1, batch), torch.int32)[:batch]
+        p = self.ptr
+        _lib.check(self.lib.nodal_lu_batched(
+            self.ctx, batch, ncomp, p(dtab["type"]), p(dtab["a"]), p(dtab["b"]), p(dtab["c"]),
+            p(dtab["d"]), p(dtab["drv"]), p(dtab["branch"]), table.kcl, n, p(values), p(x),
+            p(info), self.stream()), "nodal_lu_batched")
+        return x, info

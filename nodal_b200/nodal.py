@@ -1,0 +1,352 @@
+"""Host-side mirror of the reference's central module (nodal/nodal.py) for the MNA hot path.
+
+Same classes and call signatures as the reference --
+
+    from nodal_b200 import Circuit, Netlist
+    solution = Circuit(Netlist("netlist.csv"), sparse=True).solve()
+    print(solution)
+
+-- but numbering produces a struct-of-arrays component table, stamping and the
+linear solve run as sm_100a CUDA kernels through libnodal_b200.so, and nothing on
+this path falls back to numpy / scipy arithmetic.
+
+Reference lines mirrored: find_ground_node nodal.py:30-42, build_opmodel :45-85,
+is_connected :88-105, Component :112-178, Netlist :181-296, Circuit :299-398,
+Solution :401-434.
+"""
+from __future__ import annotations
+
+import csv
+import logging
+import os
+import warnings
+
+import numpy as np
+
+from . import constants as c
+from . import models
+from .table import ComponentTable
+
+logging.basicConfig(level=logging.ERROR)  # as the reference does at import (nodal.py:27)
+
+__all__ = ["find_ground_node", "build_opmodel", "is_connected", "UnconnectedCircuitError",
+           "Component", "Netlist", "Circuit", "Solution", "c", "models", "np", "logging"]
+
+
+def find_ground_node(degrees):
+    """Node used as the 0 V reference: "g" when present, otherwise the first node
+    (insertion order) with the largest number of attached leads."""
+    if "g" in degrees:
+        ground = "g"
+    else:
+        ground = max(degrees.keys(), key=degrees.__getitem__)
+    logging.debug(f"ground node-> {ground}")
+    return ground
+
+
+def build_opmodel(data):
+    """Expand an OPMODEL row [name, "OPMODEL", rf, out, gnd, pos, neg] into the
+    macro model: input resistor, output resistor, VCVS and (unless rf is the
+    string "0") the feedback resistor.  Values go through str() exactly as in the
+    reference so that float() later parses the same digits."""
+    name, rf = data[c.NCOL], data[c.VCOL]
+    out, gnd, pos, neg = data[c.ACOL], data[c.BCOL], data[c.CCOL], data[c.DCOL]
+    inner = f"{name}_internal_node"
+    parts = [
+        [f"{name}_ri", "R", str(c.OPMODEL_RI), pos, neg],
+        [f"{name}_ro", "R", str(c.OPMODEL_RO), inner, out],
+        [f"{name}_vcvs", "VCVS", str(c.OPMODEL_GAIN), inner, gnd, pos, neg],
+    ]
+    if rf != "0":
+        parts.append([f"{name}_rf", "R", rf, neg, out])
+    else:
+        assert neg == out
+    return parts
+
+
+def is_connected(netlist):
+    """True when every node can be reached from ground through component leads
+    (control nodes do not count).  Diagnostic for singular systems only."""
+    adjacency = {node: set() for node in netlist.degrees}
+    for comp in netlist.components.values():
+        adjacency[comp.anode].add(comp.bnode)
+        adjacency[comp.bnode].add(comp.anode)
+    seen = {netlist.ground}
+    frontier = [netlist.ground]
+    while frontier:
+        nxt = []
+        for node in frontier:
+            for other in adjacency[node]:
+                if other not in seen:
+                    seen.add(other)
+                    nxt.append(other)
+        frontier = nxt
+    return len(seen) == len(adjacency)
+
+
+class UnconnectedCircuitError(Exception):
+    pass
+
+
+class Component:
+    """One electrical component, built from a csv row (list of str).
+
+    Attributes: name, type, value, anode, bnode, pos_control, neg_control and,
+    for dependent sources only, driver (None unless current controlled).
+    Raises ValueError on malformed rows.
+    """
+
+    def __init__(self, data):
+        self.check_input(data)
+        self.name = data[c.NCOL]
+        self.type = data[c.TCOL]
+        self.value = float(data[c.VCOL])
+        self.anode = data[c.ACOL]
+        self.bnode = data[c.BCOL]
+        self.pos_control = None
+        self.neg_control = None
+        if self.type in c.NODE_TYPES_DEP:
+            self.pos_control = data[c.CCOL]
+            self.neg_control = data[c.DCOL]
+            self.driver = data[c.PCOL] if self.type in c.NODE_TYPES_CC else None
+
+    def check_input(self, data):
+        n_fields = len(data)
+        if n_fields == 0 or data[0][0] == "#":
+            return
+        key = data[c.NCOL]
+        assert type(key) == str
+        if n_fields < 5:
+            raise ValueError(f"Missing arguments for component {key}")
+        ctype = data[c.TCOL]
+        if ctype not in c.NODE_TYPES:
+            raise ValueError(f"Unknown type {ctype} for component {key}")
+        expected = c.NODE_ARGS_NUMBER[ctype]
+        if n_fields != expected:
+            raise ValueError(
+                f"Wrong number of arguments for component {key}: expected {expected}, got {n_fields}")
+        try:
+            float(data[c.VCOL])
+        except ValueError:
+            raise ValueError("Bad input: expected a number for component value "
+                             f"of {key}, got {data[c.VCOL]} instead")
+
+
+class Netlist:
+    """Reads a netlist from a .csv file and numbers its unknowns.
+
+    Attributes (same meaning as the reference): nums, degrees, anomnum,
+    components, component_keys, ground, nodenum, opmodel_equivalents.
+    ``table()`` additionally returns the struct-of-arrays component table the
+    stamp kernel consumes.
+    Raises FileNotFoundError / ValueError like the reference.
+    """
+
+    def __init__(self, path):
+        self.nums = {"components": 0, "anomalies": 0, "be": 0, "kcl": 0, "opamps": 0}
+        self.degrees = {}
+        self.anomnum = {}
+        self.components = {}
+        self.component_keys = []
+        self.ground = None
+        self.nodenum = {}
+        self.opmodel_equivalents = []
+        self.read_netlist(path)
+
+    # ---- numbering -------------------------------------------------------------
+    def process_component(self, data):
+        """Register one csv row: component record, node degrees, branch number."""
+        if data == [] or data[0][0] == "#":
+            return
+        if data[c.TCOL] == "OPMODEL":           # expanded now, registered after all rows
+            self.opmodel_equivalents.extend(build_opmodel(data))
+            return
+        comp = Component(data)
+        key = data[c.NCOL]
+        self.component_keys.append(key)         # duplicates are kept on purpose (stamping order)
+        self.components[key] = comp
+        self.nums["components"] += 1
+        leads = [data[c.ACOL], data[c.BCOL]]
+        unseen = [node for node in leads if node not in self.degrees]
+        if data[c.TCOL] in c.NODE_TYPES_ANOM:
+            self.anomnum[key] = self.nums["anomalies"]
+            self.nums["anomalies"] += 1
+        for node in unseen:
+            self.degrees[node] = 0
+        for node in leads:
+            self.degrees[node] += 1
+
+    def read_netlist(self, path):
+        try:
+            handle = open(path, "r")
+        except FileNotFoundError:
+            logging.error(f"File '{path}' not found.")
+            raise
+        with handle:
+            for row in csv.reader(handle, skipinitialspace=True):
+                self.process_component(row)
+        for row in self.opmodel_equivalents:
+            self.process_component(row)
+        self._number_nodes()
+
+    def _number_nodes(self):
+        self.ground = find_ground_node(self.degrees)
+        self.nodenum = {}
+        for node in self.degrees:
+            if node != self.ground:
+                self.nodenum[node] = len(self.nodenum)
+        assert len(self.nodenum) == len(self.degrees) - 1
+        logging.debug(f"nodenum={self.nodenum}")
+        self.nums["kcl"] = len(self.nodenum)
+        self.nums["be"] = self.nums["anomalies"]
+        logging.debug(f"nums={self.nums}")
+        logging.debug(f"anomnum={self.anomnum}")
+
+    # ---- B200 build: component table --------------------------------------------
+    def is_resistive(self):
+        return all(comp.type == "R" for comp in self.components.values())
+
+    def table(self) -> ComponentTable:
+        """Component table in stamping order.  Goes through the same dispatch as the
+        reference's build_model (nodal.py:357-390) with a recorder in place of G."""
+        return self.table_and_currents()[0]
+
+    def table_and_currents(self):
+        rec = models.StampRecorder(self)
+        self._dispatch(rec)
+        return rec.finish(), rec.currents
+
+    def _dispatch(self, G):
+        nums, anomnum, nodenum = self.nums, self.anomnum, self.nodenum
+        ground, components = self.ground, self.components
+        A, currents = G.rhs_proxy, G.currents
+        for key in self.component_keys:
+            comp = components[key]
+            i = nodenum[comp.anode] if comp.anode != ground else None
+            j = nodenum[comp.bnode] if comp.bnode != ground else None
+            args = (comp, i, j, ground, G, A, currents, anomnum, nums, nodenum)
+            kind = comp.type
+            if kind == "R":
+                models.write_R(comp, i, j, ground, G)
+            elif kind == "A":
+                models.write_A(comp, i, j, ground, A)
+            elif kind == "E":
+                models.write_E(*args)
+            elif kind == "VCCS":                 # the reference stamps VCCS as a VCVS (nodal.py:377-378)
+                models.write_VCVS(*args)
+            elif kind == "VCVS":
+                models.write_VCVS(*args)
+            elif kind == "CCVS":
+                models.write_CCVS(*args, components)
+            elif kind == "CCCS":
+                models.write_CCCS(*args, components)
+            elif kind == "OPAMP":
+                raise NotImplementedError
+            else:
+                raise ValueError(f"Unknown component type: {kind}")
+
+
+class Circuit:
+    """Builds and solves the MNA system  G e = A  of a Netlist on the GPU.
+
+    ``sparse=False``: dense G, blocked FP64 LU with partial pivoting (replaces
+    numpy.linalg.solve).  ``sparse=True``: CSR G, Jacobi-PCG for R/A-only
+    netlists, restarted GMRES otherwise (replaces scipy spsolve).
+
+    Attributes as in the reference: netlist, sparse, G, A, currents.  G and A
+    live in HBM; ``G`` is a torch tensor (dense) or a DeviceCSR, and
+    ``np.asarray(circuit.G)`` / ``circuit.G.tocsr()`` / ``circuit.A_host`` give host
+    copies.
+    """
+
+    def __init__(self, netlist, sparse=False, **options):
+        if not isinstance(netlist, Netlist):
+            raise TypeError("Input isn't a netlist")
+        self.netlist = netlist
+        self.sparse = sparse
+        self.options = options
+        self.stats = {}
+        self.G, self.A, self.currents = self.build_model()
+
+    # ---- assembly ---------------------------------------------------------------
+    def build_model(self):
+        from .device import Device
+        table, currents = self.netlist.table_and_currents()
+        table.validate()
+        self.table = table
+        dev = Device.get(self.options.get("device"))
+        self._dev = dev
+        if self.sparse:
+            G, A = dev.assemble_csr(table)
+        else:
+            G, A = dev.assemble_dense(table, atomic=bool(self.options.get("atomic_stamp", False)))
+        logging.debug(f"currents={currents}")
+        return [G, A, currents]
+
+    @property
+    def A_host(self):
+        return self.A.cpu().numpy()
+
+    @property
+    def G_host(self):
+        if self.sparse:
+            return self.G.tocsr()
+        return self.G.cpu().numpy()
+
+    # ---- solve ------------------------------------------------------------------
+    def solve(self):
+        """Raises numpy.linalg.LinAlgError (singular dense system) or
+        UnconnectedCircuitError (floating nodes), as the reference does."""
+        dev = self._dev
+        if self.sparse:
+            rtol = self.options.get("rtol", 1e-10)
+            if self.table.is_spd_structured():
+                x, info = dev.pcg(self.G, self.A, rtol=rtol, maxit=self.options.get("maxit"),
+                                  flags=self.options.get("pcg_flags", 0))
+            else:
+                x, info = dev.gmres(self.G, self.A, rtol=self.options.get("rtol", 1e-12),
+                                    restart=self.options.get("restart", 60),
+                                    maxit=self.options.get("maxit") or 20000)
+            e = x.cpu().numpy()
+            if info["status"] != 0:
+                # the reference's sparse path does not raise on singular systems: scipy warns
+                # (MatrixRankWarning) and returns NaNs.  Mirror that.
+                warnings.warn(f"sparse solve did not converge ({info})", RuntimeWarning)
+                if info["status"] == 3 or not np.all(np.isfinite(e)):
+                    e = np.full_like(e, np.nan)
+        else:
+            work = self.G.clone()
+            x, info = dev.lu_solve(work, self.A)
+            if info["status"] == 1:
+                if not is_connected(self.netlist):
+                    logging.error("Model error: unconnected circuit")
+                    raise UnconnectedCircuitError
+                logging.error("Model error: matrix is singular")
+                raise np.linalg.LinAlgError("Singular matrix")
+            e = x.cpu().numpy()
+        self.stats = info
+        sol = Solution(e, self.netlist, self.currents)
+        sol.stats = info
+        return sol
+
+
+class Solution:
+    """Result of a solve: ``result`` holds the kcl node potentials followed by the
+    branch currents.  Printable, same layout as the reference."""
+
+    def __init__(self, result, netlist, currents):
+        self.result = result
+        self.nodenum = netlist.nodenum
+        self.nums = netlist.nums
+        self.currents = currents
+        self.ground = netlist.ground
+        self.anomnum = netlist.anomnum
+        self.stats = {}
+
+    def __str__(self):
+        lines = [f"Ground node: {self.ground}"]
+        for name in sorted(self.nodenum):
+            lines.append(f"e({name}) \t= {self.result[self.nodenum[name]]}")
+        for name in sorted(self.anomnum):
+            lines.append(f"i({name}) \t= {self.result[self.nums['kcl'] + self.anomnum[name]]}")
+        return "\n".join(lines)

@@ -1,0 +1,170 @@
+"""GPU parity: SpMV kernels and the Jacobi-PCG solve against scipy / the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spla
+
+import nodal_b200 as n
+import nodal_b200.equiv
+from helpers import block_err, golden, write_csv
+from nodal_b200 import _lib
+from nodal_b200 import generators as gen
+from nodal_b200.device import DeviceCSR
+from oracle import mna_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DOC = golden("doc_netlists.json")
+GRIDS = golden("grids.json")
+PINNED = golden("pinned_by_reference_tests.json")
+
+
+def to_device_csr(device, M):
+    M = sps.csr_matrix(M)
+    M.sort_indices()
+    return DeviceCSR(M.shape[0], device.to_device(M.indptr.astype(np.int32)),
+                     device.to_device(M.indices.astype(np.int32)), device.to_device(M.data))
+
+
+def sell_spmv(device, csr, x):
+    h = C.c_void_p()
+    p = device.ptr
+    _lib.check(device.lib.nodal_sell_create(device.ctx, csr.n, csr.nnz, p(csr.indptr), p(csr.indices),
+                                            p(csr.data), C.byref(h), device.stream()), "sell_create")
+    y = device.empty(max(1, csr.n), device.torch.float64)[: csr.n]
+    _lib.check(device.lib.nodal_sell_spmv(device.ctx, h, p(x), p(y), device.stream()), "sell_spmv")
+    device.torch.cuda.synchronize()
+    padded = device.lib.nodal_sell_padded_nnz(h)
+    device.lib.nodal_sell_destroy(h)
+    return y, padded
+
+
+@pytest.mark.parametrize("nrow,density,seed", [(1, 1.0, 0), (31, 0.2, 1), (33, 0.05, 2), (1000, 0.0015, 3),
+                                               (5000, 0.001, 4), (20000, 0.0005, 5), (3000, 0.013, 6),
+                                               (2000, 0.1, 7)])
+def test_spmv_matches_scipy(device, nrow, density, seed):
+    rng = np.random.default_rng(seed)
+    M = sps.random(nrow, nrow, density=density, random_state=rng, format="csr") + sps.eye(nrow) * (seed % 2)
+    M = sps.csr_matrix(M)
+    x = rng.standard_normal(nrow)
+    want = M @ x
+    scale = np.abs(M) @ np.abs(x) + 1e-300
+    csr = to_device_csr(device, M)
+    xd = device.to_device(x)
+    y = device.spmv(csr, xd).cpu().numpy()
+    assert np.max(np.abs(y - want) / scale) < 1e-15 * 8
+    y2, padded = sell_spmv(device, csr, xd)
+    assert np.max(np.abs(y2.cpu().numpy() - want) / scale) < 1e-15 * 8
+    assert padded >= M.nnz and padded % 32 == 0
+
+
+def test_spmv_grid_matrix_exact(device):
+    """1-ohm grid: every product is exact in FP64, so both kernels must equal scipy bit for bit."""
+    csr, _ = device.assemble_csr(gen.grid2d(64).table())
+    x = np.arange(csr.n, dtype=np.float64) % 17 - 8
+    want = csr.tocsr() @ x
+    xd = device.to_device(x)
+    assert np.array_equal(device.spmv(csr, xd).cpu().numpy(), want)
+    assert np.array_equal(sell_spmv(device, csr, xd)[0].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("name", sorted(PINNED["equiv"]))
+def test_reference_tests_equivalent_resistance(device, name, tmp_path):
+    """tests.py:24-29 through the sparse (PCG) path."""
+    net = n.Netlist(write_csv(DOC[name]["rows"], tmp_path / name))
+    r = n.equiv.equivalent_resistance(net, "1", "g", sparse=True)
+    assert r == pytest.approx(PINNED["equiv"][name], rel=1e-9)
+
+
+@pytest.mark.parametrize("key", ["grid2d_6", "grid2d_20", "grid2d_50", "grid2d_100", "lattice3d_5", "lattice3d_6"])
+def test_equivalent_resistance_matches_reference(device, key):
+    g = GRIDS[key]
+    tn = gen.grid2d(g["N"]) if key.startswith("grid2d") else gen.lattice3d(g["N"])
+    r = n.equiv.equivalent_resistance(tn, "1", "g", sparse=True)
+    stats = n.equiv.equivalent_resistance.last_stats
+    assert stats["status"] == 0 and stats["relres"] <= 1e-10
+    assert r == pytest.approx(g["R_sparse"], rel=1e-9)          # north star: 1e-9 relative
+
+
+@pytest.mark.parametrize("flags", [0, _lib.PCG_FORCE_CSR, _lib.PCG_NO_GRAPH, _lib.PCG_FORCE_CSR | _lib.PCG_NO_GRAPH])
+def test_pcg_full_vector_against_oracle(device, flags):
+    N = 60
+    tn = gen.grid2d(N)
+    import copy
+    probe = copy.deepcopy(tn)
+    probe.process_component(["a1", "A", "1", "1", "g"])
+    csr, rhs = device.assemble_csr(probe.table())
+    x, info = device.pcg(csr, rhs, rtol=1e-12, flags=flags)
+    assert info["status"] == 0 and info["relres"] <= 1e-12
+    assert info["format"] == ("csr" if flags & _lib.PCG_FORCE_CSR else "sell32")
+    G = csr.tocsr()
+    b = rhs.cpu().numpy()
+    want = spla.spsolve(G.tocsc(), b)
+    x = x.cpu().numpy()
+    assert np.max(np.abs(x - want)) / np.max(np.abs(want)) < 1e-9
+    assert np.linalg.norm(G @ x - b) / np.linalg.norm(b) <= 1e-11
+
+
+def test_pcg_is_deterministic(device):
+    csr, rhs = device.assemble_csr(gen.grid2d(80).table())
+    b = device.to_device(np.random.default_rng(0).standard_normal(csr.n))
+    x1, i1 = device.pcg(csr, b, rtol=1e-10)
+    x2, i2 = device.pcg(csr, b, rtol=1e-10)
+    assert i1["iterations"] == i2["iterations"]
+    assert device.torch.equal(x1, x2)
+
+
+def test_pcg_random_spd_and_irregular_rows(device):
+    """Graph Laplacian of a random graph with a few hub nodes (long rows -> wide slices)."""
+    rng = np.random.default_rng(5)
+    m = 4000
+    i = rng.integers(0, m, 12000); j = rng.integers(0, m, 12000)
+    i = np.concatenate([i, np.zeros(1500, int), np.full(700, 7)]); j = np.concatenate([j, rng.integers(0, m, 2200)])
+    w = rng.uniform(0.1, 10, len(i))
+    keep = i != j
+    i, j, w = i[keep], j[keep], w[keep]
+    L = sps.coo_matrix((np.concatenate([w, w, -w, -w]), (np.concatenate([i, j, i, j]), np.concatenate([i, j, j, i]))),
+                       shape=(m, m)).tocsr() + sps.eye(m) * 0.01
+    b = rng.standard_normal(m)
+    csr = to_device_csr(device, L)
+    for flags in (0, _lib.PCG_FORCE_CSR):
+        x, info = device.pcg(csr, device.to_device(b), rtol=1e-11, flags=flags)
+        assert info["status"] == 0
+        x = x.cpu().numpy()
+        assert np.linalg.norm(L @ x - b) / np.linalg.norm(b) <= 1.01e-11
+        assert np.max(np.abs(x - spla.spsolve(L.tocsc(), b))) / np.max(np.abs(x)) < 1e-8
+
+
+def test_pcg_edge_cases(device):
+    # zero right-hand side -> zero solution, 0 iterations
+    csr, rhs = device.assemble_csr(gen.grid2d(10).table())
+    x, info = device.pcg(csr, rhs)
+    assert info["status"] == 0 and info["iterations"] == 0 and not x.cpu().numpy().any()
+    # 1 x 1 and odd-sized systems
+    for m in (1, 2, 3, 33):
+        A = sps.diags([np.full(m, 4.0), np.full(m - 1, -1.0), np.full(m - 1, -1.0)], [0, 1, -1]).tocsr() \
+            if m > 1 else sps.csr_matrix([[4.0]])
+        b = np.arange(1, m + 1, dtype=float)
+        x, info = device.pcg(to_device_csr(device, A), device.to_device(b), rtol=1e-13)
+        assert info["status"] == 0
+        assert np.allclose(A @ x.cpu().numpy(), b, rtol=1e-12)
+    # indefinite matrix -> breakdown is reported, no exception, no hang
+    A = sps.diags([[1.0, -1.0, 2.0, -3.0]], [0]).tocsr()
+    x, info = device.pcg(to_device_csr(device, A), device.to_device(np.ones(4)))
+    assert info["status"] == _lib.BREAKDOWN
+    # maxit is honoured
+    csr, _ = device.assemble_csr(gen.grid2d(100).table())
+    b = device.to_device(np.random.default_rng(1).standard_normal(csr.n))
+    x, info = device.pcg(csr, b, rtol=1e-14, maxit=7)
+    assert info["status"] == _lib.NOT_CONVERGED and info["iterations"] == 7
+
+
+@pytest.mark.parametrize("N,want", [(400, 0.7732566450916762), (1000, 0.7732422803670024)])
+def test_equivalent_resistance_config_c2(device, N, want):
+    """Config C2 (and its 400^2 sibling): golden values are the reference's own end-to-end
+    results, far beyond what the oracle can redo in seconds."""
+    r = n.equiv.equivalent_resistance(gen.grid2d(N), "1", "g", sparse=True)
+    stats = n.equiv.equivalent_resistance.last_stats
+    assert stats["status"] == 0 and stats["relres"] <= 1e-10
+    assert r == pytest.approx(want, rel=1e-9)

@@ -49,6 +49,9 @@ typedef struct nodal_ctx nodal_ctx;
 
 int nodal_abi_version(void);
 const char* nodal_last_error(void);
+/* number of kernels this library has launched so far in this process (graph nodes count
+ * once per graph launch) */
+uint64_t nodal_launch_count(void);
 int nodal_ctx_create(int device, nodal_ctx** out);
 int nodal_ctx_destroy(nodal_ctx* ctx);
 /* bytes of device scratch currently held by the ctx */
@@ -120,14 +123,17 @@ int nodal_sell_spmv(nodal_ctx* ctx, const nodal_sell* m, const double* x, double
  * scipy.sparse.linalg.spsolve at nodal/nodal.py:325 for SPD (R / A only) netlists.
  * x holds the initial guess on entry and the solution on exit.  Converged when
  * ||b - A x||_2 <= rtol * ||b||_2 (checked on the true residual at the end).
- * stats_h (optional, 8 doubles): [0] iterations, [1] relres (true), [2] restarts,
- * [3] solve ms (device), [4] setup ms, [5] format (0 csr, 1 sell), [6] padded nnz, [7] -. */
+ * stats_h (optional, 16 doubles): [0] iterations, [1] relres (true), [2] restarts,
+ * [3] solve ms (device), [4] setup ms, [5] format (0 csr, 1 sell), [6] stored nnz,
+ * [7] SpMV grid size; with NODAL_PCG_PROFILE: [8..10] mean ms of the spmv_dot / update /
+ * direction kernels, [11] launches averaged over. */
 int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
               const int32_t* indices, const double* data, const double* rhs, double* x,
               double rtol, int32_t maxit, int32_t flags,
               int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
 #define NODAL_PCG_FORCE_CSR 1   /* do not build the sliced-ELL copy          */
-#define NODAL_PCG_NO_GRAPH 2    /* launch kernels directly (debug / profile) */
+#define NODAL_PCG_NO_GRAPH 2    /* launch kernels directly (debug)           */
+#define NODAL_PCG_PROFILE 4     /* direct launches, every kernel bracketed by CUDA events */
 
 /* Restarted GMRES(m) with diagonal (zero-safe) right preconditioning, FP64.
  * Replaces spsolve at nodal/nodal.py:325 when controlled / voltage sources make

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnodal_b200.so")
 
 OK, SINGULAR, NOT_CONVERGED, BREAKDOWN, CUDA_ERROR, BAD_ARG = 0, 1, 2, 3, 4, -1
-PCG_FORCE_CSR, PCG_NO_GRAPH = 1, 2
+PCG_FORCE_CSR, PCG_NO_GRAPH, PCG_PROFILE = 1, 2, 4
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 
@@ -20,6 +20,7 @@ _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     "nodal_abi_version": (C.c_int, []),
     "nodal_last_error": (C.c_char_p, []),
+    "nodal_launch_count": (C.c_uint64, []),
     "nodal_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "nodal_ctx_destroy": (C.c_int, [_vp]),
     "nodal_ctx_workspace_bytes": (_i64, [_vp]),

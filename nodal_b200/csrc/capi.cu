@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_nodal_launches = 0;
 
 void nodal_set_error(const char* fmt, ...) {
     va_list ap;
@@ -14,6 +15,7 @@ void nodal_set_error(const char* fmt, ...) {
 
 extern "C" int nodal_abi_version(void) { return NODAL_ABI_VERSION; }
 extern "C" const char* nodal_last_error(void) { return g_err; }
+extern "C" uint64_t nodal_launch_count(void) { return g_nodal_launches; }
 
 extern "C" int nodal_ctx_create(int device, nodal_ctx** out) {
     if (!out) return NODAL_BAD_ARG;

@@ -32,7 +32,12 @@ void nodal_set_error(const char* fmt, ...);
         if (_s != NODAL_OK) return _s;                                                   \
     } while (0)
 
-#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+extern unsigned long long g_nodal_launches;  // kernels launched by this library (host counter)
+#define KERNEL_CHECK()                 \
+    do {                               \
+        ++g_nodal_launches;            \
+        CUDA_TRY(cudaGetLastError());  \
+    } while (0)
 
 // A grow-only device scratch arena.  Each API call opens a Scope, carves what it
 // needs and everything is handed back when the Scope dies.  If the arena is too

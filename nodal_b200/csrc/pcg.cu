@@ -305,7 +305,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
     if (!ctx || n < 0 || !iters_h || !relres_h) return NODAL_BAD_ARG;
     *iters_h = 0;
     *relres_h = 0.0;
-    if (stats_h) memset(stats_h, 0, 8 * sizeof(double));
+    if (stats_h) memset(stats_h, 0, 16 * sizeof(double));
     if (n == 0) return NODAL_OK;
     if (((uintptr_t)x & 15) || ((uintptr_t)rhs & 15)) {
         nodal_set_error("nodal_pcg: x and rhs must be 16-byte aligned");
@@ -327,6 +327,8 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
     int restarts = 0;
     PcgDev host{};
     float ms_setup = 0.f, ms_solve = 0.f;
+    std::vector<cudaEvent_t> prof_ev;
+    double prof_ms[4] = {0, 0, 0, 0};
     // everything below funnels through `finish` so the resources above are released
     auto run = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ev_t0, st));
@@ -399,8 +401,14 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             return NODAL_OK;
         };
 
-        const bool use_graph = !(flags & NODAL_PCG_NO_GRAPH);
+        const bool profile = (flags & NODAL_PCG_PROFILE) != 0;
+        const bool use_graph = !(flags & NODAL_PCG_NO_GRAPH) && !profile;
+        if (profile) {
+            prof_ev.resize(PCG_CHUNK * 4);
+            for (auto& e : prof_ev) CUDA_TRY(cudaEventCreate(&e));
+        }
         if (use_graph) {
+            const unsigned long long before = g_nodal_launches;
             CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
             int crc = NODAL_OK;
@@ -409,6 +417,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             if (crc != NODAL_OK) return crc;
             CUDA_TRY(ce);
             CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
+            g_nodal_launches = before;  // captured nodes are counted per graph launch below
         }
         NODAL_TRY(start(1));
         CUDA_TRY(cudaEventRecord(ev_t1, st));
@@ -420,9 +429,40 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             const int64_t max_chunks = (int64_t)maxit / PCG_CHUNK + 3;
             int64_t k = 0;
             for (;; ++k) {
-                if (use_graph) CUDA_TRY(cudaGraphLaunch(gexec, st));
-                else
+                if (use_graph) {
+                    CUDA_TRY(cudaGraphLaunch(gexec, st));
+                    g_nodal_launches += 3ull * PCG_CHUNK;
+                } else if (profile) {
+                    const int it0 = host.iters;
+                    for (int i = 0; i < PCG_CHUNK; ++i) {
+                        const int par = i & 1;
+                        CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 0], st));
+                        NODAL_TRY(launch_k1(A, dev, p, q, part_pq[par], st));
+                        CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 1], st));
+                        pcg_update_kernel<<<g2, PCG_THREADS, 0, st>>>(
+                            dev, n, part_pq[par], A.g1, part_rz[par ^ 1], g2, x, p, r, q, dinv,
+                            part_rz[par], part_rr[par]);
+                        KERNEL_CHECK();
+                        CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 2], st));
+                        pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(
+                            dev, n, part_rz[par ^ 1], part_rz[par], part_rr[par], g2, p, r, dinv);
+                        KERNEL_CHECK();
+                        CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 3], st));
+                    }
+                    CUDA_TRY(cudaMemcpyAsync(&poll[0], dev, sizeof(PcgDev), cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    const int ran = poll[0].iters - it0;  // iterations that did real work
+                    for (int i = 0; i < ran && i < PCG_CHUNK; ++i) {
+                        float a = 0, b = 0, c = 0;
+                        CUDA_TRY(cudaEventElapsedTime(&a, prof_ev[4 * i + 0], prof_ev[4 * i + 1]));
+                        CUDA_TRY(cudaEventElapsedTime(&b, prof_ev[4 * i + 1], prof_ev[4 * i + 2]));
+                        CUDA_TRY(cudaEventElapsedTime(&c, prof_ev[4 * i + 2], prof_ev[4 * i + 3]));
+                        prof_ms[0] += a; prof_ms[1] += b; prof_ms[2] += c; prof_ms[3] += 1.0;
+                    }
+                    host = poll[0];
+                } else {
                     for (int i = 0; i < PCG_CHUNK; ++i) NODAL_TRY(iteration(i & 1, st));
+                }
                 CUDA_TRY(cudaMemcpyAsync(&poll[k & 1], dev, sizeof(PcgDev), cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaEventRecord(ev_poll[k & 1], st));
                 if (k >= 1) {
@@ -469,6 +509,12 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             stats_h[5] = A.sell ? 1.0 : 0.0;
             stats_h[6] = A.sell ? (double)sell->padded : (double)nnz;
             stats_h[7] = A.g1;
+            if (prof_ms[3] > 0) {
+                stats_h[8] = prof_ms[0] / prof_ms[3];
+                stats_h[9] = prof_ms[1] / prof_ms[3];
+                stats_h[10] = prof_ms[2] / prof_ms[3];
+                stats_h[11] = prof_ms[3];
+            }
         }
         return host.status;
     };
@@ -476,6 +522,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
     if (cap) cudaStreamDestroy(cap);
+    for (auto& e : prof_ev) cudaEventDestroy(e);
     if (sell) { cudaStreamSynchronize(st); sell_free(sell); }
     cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1); cudaEventDestroy(ev_t2);
     cudaEventDestroy(ev_poll[0]); cudaEventDestroy(ev_poll[1]);

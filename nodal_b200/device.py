@@ -194,7 +194,7 @@ class Device:
         if maxit is None:
             maxit = max(5000, 40 * int(np.sqrt(max(n, 1))))
         iters, relres = C.c_int32(0), C.c_double(0.0)
-        stats = (C.c_double * 8)()
+        stats = (C.c_double * 16)()
         p = self.ptr
         st = self.lib.nodal_pcg(self.ctx, n, csr.nnz, p(csr.indptr), p(csr.indices), p(csr.data),
                                 p(rhs), p(x), rtol, maxit, flags, C.byref(iters), C.byref(relres),
@@ -204,6 +204,9 @@ class Device:
                     restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4],
                     format="sell32" if stats[5] else "csr", stored_nnz=int(stats[6]),
                     spmv_grid=int(stats[7]))
+        if stats[11]:
+            info["kernel_ms"] = dict(spmv_dot=stats[8], update=stats[9], direction=stats[10],
+                                     samples=int(stats[11]))
         return x, info
 
     def gmres(self, csr: DeviceCSR, rhs, rtol=1e-12, restart=60, maxit=20000):

@@ -1,0 +1,264 @@
+// Restarted GMRES(m), FP64, right-preconditioned with the (zero-safe) diagonal.
+// Replaces scipy.sparse.linalg.spsolve (nodal/nodal.py:325) for netlists whose voltage /
+// controlled sources make G non-symmetric and put zeros on the diagonal of the branch rows
+// (nodal/models.py:35-78: write_E / write_VCVS never touch G[r, r]).
+//
+// Arnoldi with classical Gram-Schmidt applied twice (CGS2): per inner step
+//   t = D^-1 v_j ; w = A t                                      (scale + CSR SpMV)
+//   h = V^T w ; w -= V h          twice                         (multi-dot + multi-axpy)
+//   h_{j+1,j} = ||w|| ; v_{j+1} = w / h_{j+1,j}
+// Dot products are two-phase and deterministic: per-block partials, then every block of the
+// consumer kernel re-reduces them in a fixed order.  The (m+1) x m Hessenberg least-squares
+// problem is tiny and is updated with Givens rotations on the host (one D2H of <= 2m+1
+// doubles per inner step).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "sparse.cuh"
+
+constexpr int GM_T = 256;
+constexpr int GM_MAXM = 128;
+
+__global__ void __launch_bounds__(GM_T)
+gm_diag_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+               const double* __restrict__ data, double* __restrict__ dinv) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double dg = 0.0;
+        for (int32_t j = indptr[r]; j < indptr[r + 1]; ++j)
+            if (indices[j] == r) dg += data[j];
+        dinv[r] = dg != 0.0 ? 1.0 / dg : 1.0;
+    }
+}
+
+// out = a .* b
+__global__ void __launch_bounds__(GM_T)
+gm_mul_kernel(int32_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a[i] * b[i];
+}
+
+// r = b - q ; partial[blk] = sum r^2 (and partial_b[blk] = sum b^2)
+__global__ void __launch_bounds__(GM_T)
+gm_residual_kernel(int32_t n, const double* __restrict__ b, const double* __restrict__ q,
+                   double* __restrict__ r, double* __restrict__ part_rr, double* __restrict__ part_bb) {
+    __shared__ double sm[40];
+    double rr = 0.0, bb = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = b[i] - q[i];
+        r[i] = v;
+        rr = fma(v, v, rr);
+        bb = fma(b[i], b[i], bb);
+    }
+    rr = block_sum(rr, sm);
+    bb = block_sum(bb, sm);
+    if (threadIdx.x == 0) { part_rr[blockIdx.x] = rr; part_bb[blockIdx.x] = bb; }
+}
+
+// v0 = r / sqrt(sum(part_rr)) ; also publishes the two sums for the host
+__global__ void __launch_bounds__(GM_T)
+gm_normalize_kernel(int32_t n, const double* __restrict__ w, const double* __restrict__ part, int np,
+                    const double* __restrict__ part2, double* __restrict__ v, double* __restrict__ out_h) {
+    __shared__ double sm[40];
+    const double ss = reduce_partials(part, np, sm);
+    const double s2 = part2 ? reduce_partials(part2, np, sm) : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out_h[0] = ss; out_h[1] = s2; }
+    const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = w[i] * inv;
+}
+
+// partial[i][blk] = sum over the block's chunk of V_i . w, for i < nv (nv <= GM_MAXM + 1);
+// with nv == 0 computes w . w into partial[0][blk].
+__global__ void __launch_bounds__(GM_T)
+gm_multidot_kernel(int32_t n, const double* __restrict__ V, int nv, const double* __restrict__ w,
+                   double* __restrict__ partial, int np) {
+    __shared__ double sm[40];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (nv == 0) {
+        double s = 0.0;
+        for (int64_t i = i0; i < n; i += stride) s = fma(w[i], w[i], s);
+        s = block_sum(s, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+        return;
+    }
+    for (int k0 = 0; k0 < nv; k0 += 4) {
+        double s[4] = {0, 0, 0, 0};
+        const int kn = min(4, nv - k0);
+        for (int64_t i = i0; i < n; i += stride) {
+            const double wi = w[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < kn) s[k] = fma(V[(size_t)(k0 + k) * n + i], wi, s[k]);
+        }
+        for (int k = 0; k < kn; ++k) {
+            const double t = block_sum(s[k], sm);
+            if (threadIdx.x == 0) partial[(size_t)(k0 + k) * np + blockIdx.x] = t;
+        }
+    }
+}
+
+// h_i = sum(partial[i][*]) ; w -= sum_i h_i V_i ; block 0 stores h (accumulating if accumulate)
+__global__ void __launch_bounds__(GM_T)
+gm_multiaxpy_kernel(int32_t n, const double* __restrict__ V, int nv, double* __restrict__ w,
+                    const double* __restrict__ partial, int np, double* __restrict__ h_out, int accumulate) {
+    __shared__ double sm[40];
+    __shared__ double h[GM_MAXM + 1];
+    for (int k = 0; k < nv; ++k) {
+        const double t = reduce_partials(partial + (size_t)k * np, np, sm);
+        if (threadIdx.x == 0) h[k] = t;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < nv; k += blockDim.x) h_out[k] = accumulate ? h_out[k] + h[k] : h[k];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double wi = w[i];
+        for (int k = 0; k < nv; ++k) wi = fma(-h[k], V[(size_t)k * n + i], wi);
+        w[i] = wi;
+    }
+}
+
+// x += D^-1 (V y)
+__global__ void __launch_bounds__(GM_T)
+gm_update_x_kernel(int32_t n, const double* __restrict__ V, int nv, const double* __restrict__ y,
+                   const double* __restrict__ dinv, double* __restrict__ x) {
+    __shared__ double ys[GM_MAXM + 1];
+    for (int k = threadIdx.x; k < nv; k += blockDim.x) ys[k] = y[k];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nv; ++k) s = fma(ys[k], V[(size_t)k * n + i], s);
+        x[i] = fma(dinv[i], s, x[i]);
+    }
+}
+
+extern "C" int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+                           const int32_t* indices, const double* data, const double* rhs, double* x,
+                           double rtol, int32_t restart, int32_t maxit, int32_t* iters_h,
+                           double* relres_h, void* stream) {
+    if (!ctx || n < 0 || !iters_h || !relres_h) return NODAL_BAD_ARG;
+    *iters_h = 0;
+    *relres_h = 0.0;
+    if (n == 0) return NODAL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int m = std::max(1, std::min({(int)restart, GM_MAXM, (int)n}));
+    const int np = (int)std::min<int64_t>((int64_t)ctx->num_sms * 4, ((int64_t)n + GM_T - 1) / GM_T);
+    const size_t vec = align_up(sizeof(double) * (size_t)n, 256);
+    const size_t need = (size_t)(m + 1) * vec + 4 * vec + align_up(sizeof(double) * (size_t)(m + 2) * np, 256) * 2 +
+                        sizeof(double) * 4 * (GM_MAXM + 8) + (1 << 16);
+    NODAL_TRY(ctx_reserve(ctx, need));
+    double* V = carve<double>(ctx, (size_t)(m + 1) * n);
+    double* w = carve<double>(ctx, n);
+    double* t = carve<double>(ctx, n);
+    double* dinv = carve<double>(ctx, n);
+    double* partial = carve<double>(ctx, (size_t)(m + 2) * np);
+    double* part2 = carve<double>(ctx, (size_t)np);
+    double* hdev = carve<double>(ctx, GM_MAXM + 8);     // h column of the current step
+    double* ydev = carve<double>(ctx, GM_MAXM + 8);
+    double* sums = carve<double>(ctx, 8);
+    if (!V || !w || !t || !dinv || !partial || !part2 || !hdev || !ydev || !sums) return NODAL_CUDA_ERROR;
+    double* hhost = reinterpret_cast<double*>(ctx->pinned);   // 4096 B pinned: >= 2*m+8 doubles
+
+    gm_diag_kernel<<<np, GM_T, 0, st>>>(n, indptr, indices, data, dinv);
+    KERNEL_CHECK();
+
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), y(m, 0.0);
+    double bnorm = -1.0, resid = 0.0;
+    int total = 0, status = NODAL_NOT_CONVERGED;
+    const int max_cycles = std::max(1, (maxit + m - 1) / m) + 1;
+    for (int cycle = 0; cycle < max_cycles; ++cycle) {
+        // true residual r = b - A x  -> v_0
+        NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, x, t, st));
+        gm_residual_kernel<<<np, GM_T, 0, st>>>(n, rhs, t, w, partial, part2);
+        KERNEL_CHECK();
+        gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, part2, V, sums);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(hhost, sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const double beta = sqrt(hhost[0]);
+        if (bnorm < 0.0) bnorm = sqrt(hhost[1]);
+        resid = beta;
+        if (!(beta == beta)) { status = NODAL_BREAKDOWN; break; }
+        if (bnorm == 0.0) {   // b = 0 -> x = 0
+            CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
+            resid = 0.0;
+            status = NODAL_OK;
+            break;
+        }
+        if (beta <= rtol * bnorm) { status = NODAL_OK; break; }
+        if (total >= maxit) break;
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int j = 0;
+        bool lucky = false;
+        for (; j < m && total < maxit; ++j, ++total) {
+            const double* vj = V + (size_t)j * n;
+            double* vn = V + (size_t)(j + 1) * n;
+            gm_mul_kernel<<<np, GM_T, 0, st>>>(n, vj, dinv, t);
+            KERNEL_CHECK();
+            NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, t, w, st));
+            for (int pass = 0; pass < 2; ++pass) {
+                gm_multidot_kernel<<<np, GM_T, 0, st>>>(n, V, j + 1, w, partial, np);
+                KERNEL_CHECK();
+                gm_multiaxpy_kernel<<<np, GM_T, 0, st>>>(n, V, j + 1, w, partial, np, hdev, pass);
+                KERNEL_CHECK();
+            }
+            gm_multidot_kernel<<<np, GM_T, 0, st>>>(n, V, 0, w, partial, np);
+            KERNEL_CHECK();
+            gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, nullptr, vn, hdev + GM_MAXM + 2);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(hhost, hdev, sizeof(double) * (GM_MAXM + 4), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            double* hcol = &H[(size_t)j * (m + 1)];   // column j, rows 0..j+1
+            for (int i = 0; i <= j; ++i) hcol[i] = hhost[i];
+            const double hn = sqrt(hhost[GM_MAXM + 2]);
+            hcol[j + 1] = hn;
+            for (int i = 0; i < j; ++i) {   // previous rotations
+                const double a = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
+                hcol[i + 1] = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
+                hcol[i] = a;
+            }
+            const double denom = hypot(hcol[j], hcol[j + 1]);
+            if (denom == 0.0 || !(denom == denom)) { status = NODAL_BREAKDOWN; break; }
+            cs[j] = hcol[j] / denom;
+            sn[j] = hcol[j + 1] / denom;
+            hcol[j] = denom;
+            hcol[j + 1] = 0.0;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            resid = fabs(g[j + 1]);
+            if (hn <= 1e-300 * bnorm) lucky = true;
+            if (resid <= rtol * bnorm || lucky) { ++j; ++total; break; }
+        }
+        if (status == NODAL_BREAKDOWN) break;
+        // y = H(0:j,0:j)^-1 g(0:j) ; x += D^-1 V y
+        for (int i = j - 1; i >= 0; --i) {
+            double s = g[i];
+            for (int k = i + 1; k < j; ++k) s -= H[(size_t)k * (m + 1) + i] * y[k];
+            y[i] = s / H[(size_t)i * (m + 1) + i];
+        }
+        for (int i = 0; i < j; ++i) hhost[i] = y[i];
+        CUDA_TRY(cudaMemcpyAsync(ydev, hhost, sizeof(double) * (size_t)std::max(j, 1), cudaMemcpyHostToDevice, st));
+        gm_update_x_kernel<<<np, GM_T, 0, st>>>(n, V, j, ydev, dinv, x);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    *iters_h = total;
+    *relres_h = bnorm > 0.0 ? resid / bnorm : 0.0;
+    if (status == NODAL_NOT_CONVERGED) {
+        // the loop may have ended on the iteration budget right after an update: re-check
+        NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, x, t, st));
+        gm_residual_kernel<<<np, GM_T, 0, st>>>(n, rhs, t, w, partial, part2);
+        KERNEL_CHECK();
+        gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, part2, V, sums);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(hhost, sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *relres_h = bnorm > 0.0 ? sqrt(hhost[0]) / bnorm : 0.0;
+        if (*relres_h <= rtol) status = NODAL_OK;
+    }
+    return status;
+}

@@ -5,15 +5,6 @@
     nodal_set_error(name ": not implemented in this build"); \
     return NODAL_BAD_ARG
 
-extern "C" int nodal_gmres(nodal_ctx*, int32_t, int64_t, const int32_t*, const int32_t*,
-                           const double*, const double*, double*, double, int32_t, int32_t,
-                           int32_t*, double*, void*) { NOT_YET("nodal_gmres"); }
-extern "C" int nodal_lu_solve(nodal_ctx*, int32_t, double*, const double*, double*, int32_t*,
-                              void*) { NOT_YET("nodal_lu_solve"); }
-extern "C" int nodal_lu_batched(nodal_ctx*, int64_t, int32_t, const uint8_t*, const int32_t*,
-                                const int32_t*, const int32_t*, const int32_t*, const int32_t*,
-                                const int32_t*, int32_t, int32_t, const double*, double*, int32_t*,
-                                void*) { NOT_YET("nodal_lu_batched"); }
 extern "C" int nodal_dist_unique_id(uint8_t*) { NOT_YET("nodal_dist_unique_id"); }
 extern "C" int nodal_dist_create(nodal_ctx*, const uint8_t*, int32_t, int32_t, nodal_dist**) {
     NOT_YET("nodal_dist_create");

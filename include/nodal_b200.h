@@ -164,7 +164,7 @@ int nodal_lu_batched(nodal_ctx* ctx, int64_t batch, int32_t ncomp,
                      void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU
- * Row-partitioned PCG: rank k owns rows [row_begin, row_end) of the global
+ * Row-partitioned PCG: rank k owns rows [bounds[k], bounds[k+1]) of the global
  * system as a local CSR whose column indices are GLOBAL.  Halo exchange of the
  * off-rank x entries + scalar all-reduces run over NCCL (dlopen'ed libnccl.so.2).
  * The 128-byte unique id is created on rank 0 and distributed by the caller
@@ -174,9 +174,11 @@ int nodal_dist_unique_id(uint8_t id_h[128]);
 int nodal_dist_create(nodal_ctx* ctx, const uint8_t id_h[128], int32_t rank, int32_t nranks,
                       nodal_dist** out);
 int nodal_dist_destroy(nodal_dist* d);
-int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global,
-                   int32_t row_begin, int32_t row_end,
-                   const int32_t* indptr, const int32_t* indices, const double* data,
+/* bounds_h[nranks + 1]: row partition, bounds_h[0] = 0, bounds_h[nranks] = n_global (host).
+ * indptr is the local row pointer rebased to 0 (length nloc + 1), nnz = indptr[nloc].
+ * stats_h as nodal_pcg, plus [12] halo entries received, [13] entries sent per iteration. */
+int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, const int32_t* bounds_h,
+                   int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* data,
                    const double* rhs_local, double* x_local,
                    double rtol, int32_t maxit,
                    int32_t* iters_h, double* relres_h, double* stats_h, void* stream);

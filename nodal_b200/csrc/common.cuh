@@ -22,6 +22,7 @@ void nodal_set_error(const char* fmt, ...);
         if (_e != cudaSuccess) {                                                         \
             nodal_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
                             cudaGetErrorString(_e));                                     \
+            (void)cudaGetLastError(); /* clear non-sticky errors */                      \
             return NODAL_CUDA_ERROR;                                                     \
         }                                                                                \
     } while (0)

@@ -391,7 +391,7 @@ extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int sms = ctx->num_sms;
-    const int max_rows_per_cta = (227 * 1024 - 4096) / (PANEL_LD * 8) - 1;   // shared-memory limit
+    const int max_rows_per_cta = (226 * 1024 - 4096) / (PANEL_LD * 8) - 1;   // shared-memory limit
     if ((int64_t)n > (int64_t)sms * max_rows_per_cta) {
         nodal_set_error("nodal_lu_solve: n=%d exceeds the panel capacity of this build (%d)", n,
                         sms * max_rows_per_cta);
@@ -412,7 +412,7 @@ extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double
     const size_t gemm_smem = sizeof(double) * 2 * (size_t)GM_STAGE;
     const size_t trsv_smem = sizeof(double) * ((size_t)LU_NB * PANEL_LD + LU_NB);
     {
-        CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
         CUDA_TRY(cudaFuncSetAttribute(lu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
         CUDA_TRY(cudaFuncSetAttribute(lu_trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv_smem));

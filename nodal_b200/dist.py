@@ -1,0 +1,136 @@
+"""Multi-GPU path: row-partitioned Jacobi-PCG, one process per GPU.
+
+Host side only does bookkeeping: the row partition, the per-rank slice of the component
+table (every component that touches a row the rank owns, in global stamping order, so the
+local rows of G come out bit-identical to the single-GPU assembly), the NCCL unique-id
+hand-off through torch.distributed, and the call into nodal_dist_pcg (csrc/dist.cu), which
+does halo discovery, halo exchange and the all-reduces natively.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import constants as K
+from .table import ComponentTable
+
+
+def partition_rows(n, world):
+    """Contiguous, near-equal row blocks: bounds[k] .. bounds[k+1] is rank k's range."""
+    base, extra = divmod(int(n), int(world))
+    sizes = np.full(world, base, dtype=np.int64)
+    sizes[:extra] += 1
+    bounds = np.zeros(world + 1, dtype=np.int32)
+    np.cumsum(sizes, out=bounds[1:])
+    return bounds
+
+
+def local_component_table(table: ComponentTable, rb: int, re: int) -> ComponentTable:
+    """Components with a lead on a row in [rb, re), order preserved.  Only R / A rows are
+    handled (the SPD path that is partitioned); indices stay global."""
+    if not table.is_spd_structured():
+        raise NotImplementedError("row-partitioned solve is implemented for R / A netlists (PCG)")
+    a, b = table.a, table.b
+    mask = ((a >= rb) & (a < re)) | ((b >= rb) & (b < re))
+    sel = np.flatnonzero(mask)
+    return ComponentTable(table.type[sel], table.value[sel], a[sel], b[sel], table.c[sel], table.d[sel],
+                          table.drv[sel], table.branch[sel], kcl=table.kcl, be=table.be)
+
+
+def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0, device=None) -> bytes:
+    """Rank `src` sends `nbytes` bytes to everyone through torch.distributed (gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(nbytes, dtype=torch.uint8)
+    if dist.get_rank() == src:
+        buf = torch.tensor(list(payload), dtype=torch.uint8)
+    if device is not None:
+        buf = buf.to(device)
+    dist.broadcast(buf, src=src)
+    return bytes(buf.cpu().tolist())
+
+
+class DistPCG:
+    """Owns the library's NCCL communicator of this rank."""
+
+    def __init__(self, dev, rank, world):
+        self.dev, self.rank, self.world = dev, int(rank), int(world)
+        lib = dev.lib
+        ident = None
+        if self.rank == 0:
+            raw = (C.c_uint8 * 128)()
+            _lib.check(lib.nodal_dist_unique_id(raw), "nodal_dist_unique_id")
+            ident = bytes(raw)
+        if self.world > 1:
+            ident = broadcast_bytes(ident, 128, src=0, device=dev.dev)
+        h = C.c_void_p()
+        raw = (C.c_uint8 * 128).from_buffer_copy(ident)
+        _lib.check(lib.nodal_dist_create(dev.ctx, raw, self.rank, self.world, C.byref(h)), "nodal_dist_create")
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            self.dev.lib.nodal_dist_destroy(self.handle)
+            self.handle = None
+
+    def assemble_local(self, table_local: ComponentTable, bounds, dtab=None):
+        """Stamp + CSR build of the rank's components, then the rank's row slice.
+        Returns (indptr_local, indices_global, data, rhs_local)."""
+        dev = self.dev
+        rb, re = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        csr, rhs = dev.assemble_csr(table_local, dtab=dtab)
+        ip = csr.indptr[rb: re + 1]
+        s, e = int(ip[0]), int(ip[-1])
+        indptr = (ip - ip[0]).contiguous()
+        return indptr, csr.indices[s:e], csr.data[s:e], rhs[rb:re]
+
+    def solve(self, n_global, bounds, indptr, indices, data, rhs_local, rtol=1e-10, maxit=None):
+        dev, torch = self.dev, self.dev.torch
+        nloc = int(bounds[self.rank + 1] - bounds[self.rank])
+        x = dev.zeros(max(2, nloc), torch.float64)[:nloc]
+        if maxit is None:
+            maxit = max(5000, 40 * int(np.sqrt(max(n_global, 1))))
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        iters, relres = C.c_int32(0), C.c_double(0.0)
+        stats = (C.c_double * 16)()
+        p = dev.ptr
+        st = dev.lib.nodal_dist_pcg(dev.ctx, self.handle, int(n_global), b.ctypes.data_as(C.c_void_p),
+                                    int(data.numel()), p(indptr), p(indices), p(data), p(rhs_local), p(x),
+                                    rtol, maxit, C.byref(iters), C.byref(relres), stats, dev.stream())
+        _lib.check(st, "nodal_dist_pcg", allowed=(_lib.OK, _lib.NOT_CONVERGED, _lib.BREAKDOWN))
+        info = dict(solver="dist_pcg", status=st, iterations=iters.value, relres=relres.value,
+                    restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4],
+                    format="sell32" if stats[5] else "csr", stored_nnz=int(stats[6]),
+                    halo_recv=int(stats[12]), halo_send=int(stats[13]), nnz=int(data.numel()))
+        return x, info
+
+
+class GridRunner:
+    """bench.py's multi-GPU step: local stamp + CSR build + partitioned PCG + R on every rank."""
+
+    def __init__(self, dev, table, probe_row, rank, world, rtol=1e-10):
+        self.dev, self.rank, self.world, self.rtol = dev, rank, world, rtol
+        self.n = table.n
+        self.bounds = partition_rows(self.n, world)
+        rb, re = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.local = local_component_table(table, rb, re)
+        self.probe_row = int(probe_row)
+        self.owner = int(np.searchsorted(self.bounds, self.probe_row, side="right") - 1)
+        self.pcg = DistPCG(dev, rank, world)
+        self.dtab = dev.upload_table(self.local)
+
+    def step(self, _unused=None):
+        import torch.distributed as dist
+        torch = self.dev.torch
+        indptr, indices, data, rhs = self.pcg.assemble_local(self.local, self.bounds, dtab=self.dtab)
+        x, info = self.pcg.solve(self.n, self.bounds, indptr, indices, data, rhs, rtol=self.rtol)
+        r = torch.zeros(1, dtype=torch.float64, device=self.dev.dev)
+        if self.rank == self.owner:
+            r[0] = x[self.probe_row - int(self.bounds[self.rank])]
+        dist.broadcast(r, src=self.owner)
+        nnz = torch.tensor([info["nnz"]], dtype=torch.int64, device=self.dev.dev)
+        dist.all_reduce(nnz)
+        info["nnz"] = int(nnz.item())
+        return float(r.item()), info

@@ -1,0 +1,66 @@
+"""Multi-GPU parity check (not a pytest file): run under torchrun on 2+ GPUs.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_check.py [N]
+
+Every rank assembles its rows, solves the N x N grid with the partitioned PCG and the result
+is compared with the reference goldens and, for small N, with the
+single-GPU solve of rank 0."""
+import copy
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from nodal_b200 import dist as ndist
+from nodal_b200 import generators as gen
+from nodal_b200.device import Device
+
+GOLD = {20: 0.7806032927398155, 50: 0.7743468244758764, 100: 0.7735139127312641, 200: 0.7733079842386412,
+        400: 0.7732566450916762, 1000: 0.7732422803670024}
+
+
+def main():
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = Device.get(local)
+    sizes = [int(a) for a in sys.argv[1:]] or [20, 100, 400]
+    ok = True
+    for N in sizes:
+        net = copy.deepcopy(gen.grid2d(N))
+        net.process_component(["a1", "A", "1", "1", "g"])
+        table = net.table()
+        runner = ndist.GridRunner(dev, table, net.nodenum["1"], rank, world, rtol=1e-10)
+        r, info = runner.step()
+        x_loc, _ = None, None
+        msg = dict(N=N, world=world, R=r, iterations=info["iterations"], relres=info["relres"],
+                   status=info["status"], halo_recv=info["halo_recv"], solve_ms=info["solve_ms"])
+        if N in GOLD:
+            msg["rel_err_vs_reference"] = abs(r - GOLD[N]) / GOLD[N]
+            ok &= msg["rel_err_vs_reference"] < 1e-9
+        ok &= info["status"] == 0 and info["relres"] <= 1e-10
+        if rank == 0 and N <= 400:
+            csr, rhs = dev.assemble_csr(table)
+            x1, i1 = dev.pcg(csr, rhs, rtol=1e-10)
+            msg["single_gpu_R"] = float(x1[net.nodenum["1"]])
+            msg["single_gpu_iterations"] = i1["iterations"]
+            ok &= abs(msg["single_gpu_R"] - r) < 1e-9
+        runner.pcg.close()
+        if rank == 0:
+            print(json.dumps(msg), flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if flag.item() else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

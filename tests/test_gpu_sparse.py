@@ -168,3 +168,22 @@ def test_equivalent_resistance_config_c2(device, N, want):
     stats = n.equiv.equivalent_resistance.last_stats
     assert stats["status"] == 0 and stats["relres"] <= 1e-10
     assert r == pytest.approx(want, rel=1e-9)
+
+
+def test_dist_pcg_single_rank(device):
+    """The multi-GPU driver with a world of one rank (NCCL communicator of size 1, empty halo)
+    must reproduce the single-GPU solver."""
+    import copy
+    from nodal_b200 import dist as ndist
+    net = copy.deepcopy(gen.grid2d(100))
+    net.process_component(["a1", "A", "1", "1", "g"])
+    table = net.table()
+    solver = ndist.DistPCG(device, 0, 1)
+    try:
+        bounds = ndist.partition_rows(table.n, 1)
+        indptr, indices, data, rhs = solver.assemble_local(table, bounds)
+        x, info = solver.solve(table.n, bounds, indptr, indices, data, rhs, rtol=1e-10)
+    finally:
+        solver.close()
+    assert info["status"] == 0 and info["relres"] <= 1e-10 and info["halo_recv"] == 0
+    assert float(x[net.nodenum["1"]]) == pytest.approx(GRIDS["grid2d_100"]["R_sparse"], rel=1e-9)

@@ -113,6 +113,8 @@ class Device:
         return C.c_void_p(t.data_ptr())
 
     def upload_table(self, table: ComponentTable, pin=False):
+        if getattr(table, "_pinned", None):
+            return {name: t.to(self.dev, non_blocking=True) for name, t in table._pinned.items()}
         return {name: self.to_device(getattr(table, name), pin=pin)
                 for name in ("type", "value", "a", "b", "c", "d", "drv", "branch")}
 

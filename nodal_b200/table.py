@@ -27,7 +27,7 @@ MAX_TRIPLES = 6
 
 
 class ComponentTable:
-    __slots__ = tuple(n for n, _ in _COLS) + ("kcl", "be")
+    __slots__ = tuple(n for n, _ in _COLS) + ("kcl", "be", "_pinned")
 
     def __init__(self, type, value, a, b, c=None, d=None, drv=None, branch=None, kcl=0, be=0):
         n = len(type)
@@ -43,6 +43,7 @@ class ComponentTable:
         self.branch = fill(branch, -1)
         self.kcl = int(kcl)
         self.be = int(be)
+        self._pinned = None
         for name, _ in _COLS:
             if len(getattr(self, name)) != n:
                 raise ValueError(f"column {name} has wrong length")
@@ -71,6 +72,17 @@ class ComponentTable:
         cols = [np.concatenate([getattr(self, name), np.array([row[name]], dtype=dt)])
                 for name, dt in _COLS]
         return ComponentTable(*cols, kcl=self.kcl, be=self.be)
+
+    def pin_memory(self):
+        """Move the columns into page-locked host memory (torch) so uploads are async DMA."""
+        import torch
+        pinned = {}
+        for name, _ in _COLS:
+            t = torch.from_numpy(getattr(self, name)).pin_memory()
+            pinned[name] = t
+            setattr(self, name, t.numpy())
+        self._pinned = pinned
+        return self
 
     def is_resistive(self):
         return bool(np.all(self.type == K.T_R))

@@ -7,10 +7,13 @@
 //     [ owned x (nloc) | halo x (nhalo) ];
 //   - ranks tell every owner which entries they need (ncclAllGather of the count matrix,
 //     grouped ncclSend/ncclRecv of the index lists).
-// Iteration = the three single-GPU kernels (pcg_kernels.cuh) plus
-//   - one gather of the entries peers need + grouped ncclSend/ncclRecv straight into the
-//     halo tail of p (before the SpMV);
-//   - two small ncclAllReduce (p.q ; r.z and r.r) of per-rank sums.
+// Iteration (Chronopoulos-Gear single-reduction form of Jacobi-PCG, see cgcg_vector_kernel):
+//   - one fused vector kernel (p, s, x, r, u updates + partial dots),
+//   - gather of the entries peers need + grouped ncclSend/ncclRecv straight into the halo
+//     tail of u,
+//   - the single-GPU SpMV+dot kernel (pcg_kernels.cuh) on the local rows,
+//   - ONE ncclAllReduce of 3 doubles (r.u, w.u, r.r).
+// A chunk of 32 iterations, NCCL calls included, is captured in one CUDA graph.
 // The scalar results are bitwise identical on all ranks, so every rank takes the same
 // convergence decision with no extra traffic.  libnccl.so.2 is dlopen'ed: the single-GPU
 // library has no NCCL dependency.
@@ -200,6 +203,139 @@ dist_reduce_kernel(const double* __restrict__ a, const double* __restrict__ b, c
     }
 }
 
+// ---------------------------------------------------------------- single-reduction CG kernels
+// Chronopoulos-Gear form of Jacobi-PCG: one fused vector pass + one SpMV per iteration and a
+// single all-reduce of (gamma, delta, rr):
+//   beta = gamma_i / gamma_{i-1} ; alpha = gamma_i / (delta_i - beta gamma_i / alpha_{i-1})
+//   p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r
+//   w = A u ; gamma_{i+1} = r.u ; delta_{i+1} = w.u ; rr = r.r
+// SC holds two parity slots {gamma, delta, rr, alpha}; alpha == 0 in the previous slot marks the
+// first iteration after a (re)start.
+__global__ void __launch_bounds__(PCG_THREADS)
+cgcg_vector_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur, const double* __restrict__ prev,
+                   double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                   double* __restrict__ s, const double* __restrict__ w, const double* __restrict__ dinv,
+                   double* __restrict__ u, double* __restrict__ part_g, double* __restrict__ part_rr) {
+    __shared__ double sm[40];
+    if (block_done(&dev->done)) return;
+    const double g = cur[0], dl = cur[1], rr = cur[2];
+    const double gp = prev[0], ap = prev[3];
+    const bool conv = rr <= dev->tol2;
+    double beta = 0.0, den = dl;
+    if (ap != 0.0) { beta = g / gp; den = dl - beta * g / ap; }
+    const double alpha = g / den;
+    const bool bad = !(den > 0.0) || !(rr == rr);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dev->rr = rr;
+        if (conv) { dev->done = 1; dev->status = NODAL_OK; }
+        else if (bad) { dev->done = 1; dev->status = NODAL_BREAKDOWN; }
+        else { dev->iters = dev->iters + 1; cur[3] = alpha; }
+    }
+    if (conv || bad) return;
+    double lg = 0.0, lrr = 0.0;
+    const int64_t n2 = n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* s2 = reinterpret_cast<double2*>(s);
+    double2* u2 = reinterpret_cast<double2*>(u);
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 xv = x2[i], rv = r2[i], pv = p2[i], sv = s2[i];
+        const double2 wv = w2[i], dv = d2[i];
+        pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
+        sv.x = fma(beta, sv.x, wv.x);        sv.y = fma(beta, sv.y, wv.y);
+        xv.x = fma(alpha, pv.x, xv.x);       xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, sv.x, rv.x);      rv.y = fma(-alpha, sv.y, rv.y);
+        double2 uv;
+        uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
+        p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
+        lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+        lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const double pv = fma(beta, p[i], dinv[i] * r[i]);
+        const double sv = fma(beta, s[i], w[i]);
+        const double rv = fma(-alpha, sv, r[i]);
+        const double uv = dinv[i] * rv;
+        p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
+        lg = fma(rv, uv, lg);
+        lrr = fma(rv, rv, lrr);
+    }
+    lg = block_sum(lg, sm);
+    lrr = block_sum(lrr, sm);
+    if (threadIdx.x == 0) { part_g[blockIdx.x] = lg; part_rr[blockIdx.x] = lrr; }
+}
+
+// r = b - q ; u = D^-1 r ; p = s = 0 ; partial sums of r.u, r.r, b.b
+__global__ void __launch_bounds__(PCG_THREADS)
+cgcg_start_kernel(int32_t n, const double* __restrict__ b, const double* __restrict__ q,
+                  const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ u,
+                  double* __restrict__ p, double* __restrict__ s, double* __restrict__ part_g,
+                  double* __restrict__ part_rr, double* __restrict__ part_bb) {
+    __shared__ double sm[40];
+    double lg = 0.0, lrr = 0.0, lbb = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double bv = b[i];
+        const double rv = bv - q[i];
+        const double uv = rv * dinv[i];
+        r[i] = rv; u[i] = uv; p[i] = 0.0; s[i] = 0.0;
+        lg = fma(rv, uv, lg);
+        lrr = fma(rv, rv, lrr);
+        lbb = fma(bv, bv, lbb);
+    }
+    lg = block_sum(lg, sm);
+    lrr = block_sum(lrr, sm);
+    lbb = block_sum(lbb, sm);
+    if (threadIdx.x == 0) { part_g[blockIdx.x] = lg; part_rr[blockIdx.x] = lrr; part_bb[blockIdx.x] = lbb; }
+}
+
+__global__ void cgcg_reset_kernel(PcgDev* dev) {
+    if (threadIdx.x == 0) dev->done = 0;
+}
+
+// out = {sum part_g, sum part_d, sum part_rr [, sum part_bb]} ; also enforces maxit
+__global__ void __launch_bounds__(PCG_THREADS)
+cgcg_reduce_kernel(PcgDev* __restrict__ dev, const double* __restrict__ part_g, const double* __restrict__ part_rr,
+                   const double* __restrict__ part_bb, int cnt_v, const double* __restrict__ part_d, int cnt_s,
+                   double* __restrict__ out, int with_bb) {
+    __shared__ double sm[40];
+    if (block_done(&dev->done)) return;
+    const double g = reduce_partials(part_g, cnt_v, sm);
+    const double rr = reduce_partials(part_rr, cnt_v, sm);
+    const double dl = reduce_partials(part_d, cnt_s, sm);
+    const double bb = with_bb ? reduce_partials(part_bb, cnt_v, sm) : 0.0;
+    if (threadIdx.x == 0) {
+        out[0] = g; out[1] = dl; out[2] = rr;
+        if (with_bb) out[3] = bb;
+        else if (dev->iters >= dev->maxit) { dev->done = 1; dev->status = NODAL_NOT_CONVERGED; }
+    }
+}
+
+// after the start all-reduce: SC[0..3] = {gamma, delta, rr, bb}
+__global__ void cgcg_scalars_kernel(PcgDev* dev, double* SC, double rtol, int maxit, int first) {
+    if (threadIdx.x != 0) return;
+    const double rr = SC[2], bb = SC[3];
+    if (first) {
+        dev->bb = bb;
+        dev->tol2 = rtol * rtol * bb;
+        dev->iters = 0;
+        dev->maxit = maxit;
+    }
+    SC[3] = 0.0;       // alpha of parity 0 (written by the first vector pass)
+    SC[4] = 1.0;       // gamma_{-1}
+    SC[7] = 0.0;       // alpha_{-1} == 0 marks "first iteration"
+    dev->rr = rr;
+    dev->status = NODAL_OK;
+    dev->done = 0;
+    if (rr <= dev->tol2) dev->done = 1;
+    else if (dev->iters >= dev->maxit) { dev->done = 1; dev->status = NODAL_NOT_CONVERGED; }
+    else if (!(rr == rr)) { dev->done = 1; dev->status = NODAL_BREAKDOWN; }
+}
+
 static int grid_of(nodal_ctx* ctx, int64_t work) {
     int64_t b = (work + DT - 1) / DT;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -242,6 +378,10 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     int restarts = 0;
     float ms_setup = 0.f, ms_solve = 0.f;
     int64_t halo_total = 0, send_total = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t cap = nullptr;
+    unsigned long long launches_per_chunk = 0;
 
     auto run = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ev0, st));
@@ -361,38 +501,41 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         const int gmax = std::max(A.g1, g2);
         const size_t vloc = align_up(sizeof(double) * (size_t)nloc, 256);
         const size_t vext = align_up(sizeof(double) * (size_t)(nloc + nhalo + 2), 256);
-        NODAL_TRY(ctx_reserve(ctx, 3 * vloc + 2 * vext + 8 * align_up(sizeof(double) * gmax, 256) + 8192));
+        NODAL_TRY(ctx_reserve(ctx, 6 * vloc + 2 * vext + 8 * align_up(sizeof(double) * gmax, 256) + 8192));
         double* r = carve<double>(ctx, nloc);
-        double* q = carve<double>(ctx, nloc);
-        double* p = carve<double>(ctx, (size_t)nloc + nhalo + 2);      // [owned | halo]
-        double* xe = carve<double>(ctx, (size_t)nloc + nhalo + 2);     // x in the same layout (residual checks)
-        double* part_pq = carve<double>(ctx, gmax);
-        double* part_rz = carve<double>(ctx, gmax);
+        double* q = carve<double>(ctx, nloc);                           // A x (residual checks)
+        double* p = carve<double>(ctx, nloc);
+        double* s = carve<double>(ctx, nloc);                           // s = A p (recurrence)
+        double* w = carve<double>(ctx, nloc);                           // w = A u
+        double* u = carve<double>(ctx, (size_t)nloc + nhalo + 2);       // u = D^-1 r, [owned | halo]
+        double* xe = carve<double>(ctx, (size_t)nloc + nhalo + 2);      // x in the same layout
+        double* part_g = carve<double>(ctx, gmax);
+        double* part_d = carve<double>(ctx, gmax);
         double* part_rr = carve<double>(ctx, gmax);
         double* part_bb = carve<double>(ctx, gmax);
-        double* S = carve<double>(ctx, 16);    // S[par*3 + {pq, rz, rr}], S[8..10] start sums
+        double* SC = carve<double>(ctx, 16);    // SC[par*4 + {gamma, delta, rr, alpha}]
         PcgDev* dev = carve<PcgDev>(ctx, 1);
         double* dinv_own = A.sell ? nullptr : carve<double>(ctx, nloc);
-        if (!r || !q || !p || !xe || !part_bb || !S || !dev) return NODAL_CUDA_ERROR;
+        if (!r || !q || !p || !s || !w || !u || !xe || !part_bb || !SC || !dev) return NODAL_CUDA_ERROR;
         const double* dinv = A.sell ? sell->dinv : dinv_own;
         if (dinv_own) {
             csr_dinv_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, indptr, lcols, data, dinv_own);
             KERNEL_CHECK();
         }
         CUDA_TRY(cudaMemsetAsync(dev, 0, sizeof(PcgDev), st));
-        CUDA_TRY(cudaMemsetAsync(S, 0, sizeof(double) * 16, st));
+        CUDA_TRY(cudaMemsetAsync(SC, 0, sizeof(double) * 16, st));
 
-        auto exchange = [&](double* v) -> int {   // fills v[nloc .. nloc+nhalo) from the owners
+        auto exchange = [&](double* v, cudaStream_t sx) -> int {   // fills v[nloc ..) from the owners
             if (R == 1) return NODAL_OK;
             if (send_total) {
-                dist_gather_kernel<<<grid_of(ctx, send_total), DT, 0, st>>>(send_total, send_idx, v, send_buf);
+                dist_gather_kernel<<<grid_of(ctx, send_total), DT, 0, sx>>>(send_total, send_idx, v, send_buf);
                 KERNEL_CHECK();
             }
             NCCL_TRY(g_nccl.GroupStart());
             for (int o = 0; o < R; ++o) {
                 if (o == me) continue;
-                if (send_cnt[o]) NCCL_TRY(g_nccl.Send(send_buf + send_off[o], send_cnt[o], ncclFloat64, o, d->comm, st));
-                if (need_from[o]) NCCL_TRY(g_nccl.Recv(v + nloc + need_off[o], need_from[o], ncclFloat64, o, d->comm, st));
+                if (send_cnt[o]) NCCL_TRY(g_nccl.Send(send_buf + send_off[o], send_cnt[o], ncclFloat64, o, d->comm, sx));
+                if (need_from[o]) NCCL_TRY(g_nccl.Recv(v + nloc + need_off[o], need_from[o], ncclFloat64, o, d->comm, sx));
             }
             NCCL_TRY(g_nccl.GroupEnd());
             return NODAL_OK;
@@ -401,50 +544,67 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             if (A.sell) return nodal_sell_spmv(ctx, A.sell, in, out, st);
             return csr_spmv_launch(ctx, nloc, nnz, indptr, lcols, data, in, out, st);
         };
+        // (re)start from the current x: r = b - A x, u = D^-1 r, w = A u, p = s = 0
         auto start = [&](int first) -> int {
+            cgcg_reset_kernel<<<1, 32, 0, st>>>(dev);
+            KERNEL_CHECK();
             CUDA_TRY(cudaMemcpyAsync(xe, x_local, sizeof(double) * (size_t)nloc, cudaMemcpyDeviceToDevice, st));
-            NODAL_TRY(exchange(xe));
+            NODAL_TRY(exchange(xe, st));
             NODAL_TRY(spmv_plain(xe, q));
-            pcg_start_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, rhs_local, q, dinv, r, p, part_rz, part_rr, part_bb);
+            cgcg_start_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, rhs_local, q, dinv, r, u, p, s, part_g, part_rr, part_bb);
             KERNEL_CHECK();
-            dist_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, part_bb, g2, S + 8);
+            NODAL_TRY(exchange(u, st));
+            NODAL_TRY(launch_k1(A, dev, u, w, part_d, st));
+            cgcg_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(dev, part_g, part_rr, part_bb, g2, part_d, A.g1, SC, 1);
             KERNEL_CHECK();
-            NCCL_TRY(g_nccl.AllReduce(S + 8, S + 8, 3, ncclFloat64, ncclSum, d->comm, st));
-            // rz of the "previous" iteration lives in the odd-parity slot
-            CUDA_TRY(cudaMemcpyAsync(S + 3 + 1, S + 8, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            pcg_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(dev, S + 9, S + 10, 1, rtol, maxit, first);
+            if (R > 1) NCCL_TRY(g_nccl.AllReduce(SC, SC, 4, ncclFloat64, ncclSum, d->comm, st));
+            cgcg_scalars_kernel<<<1, 32, 0, st>>>(dev, SC, rtol, maxit, first);
             KERNEL_CHECK();
             return NODAL_OK;
         };
-        auto iteration = [&](int par) -> int {
-            double* Sp = S + par * 3;
-            double* Sq = S + (par ^ 1) * 3;
-            NODAL_TRY(exchange(p));
-            NODAL_TRY(launch_k1(A, dev, p, q, part_pq, st));
-            dist_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(part_pq, nullptr, nullptr, A.g1, Sp);
+        auto iteration = [&](int par, cudaStream_t sx) -> int {
+            double* cur = SC + par * 4;
+            double* nxt = SC + (par ^ 1) * 4;
+            cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
+                                                          part_g, part_rr);
             KERNEL_CHECK();
-            NCCL_TRY(g_nccl.AllReduce(Sp, Sp, 1, ncclFloat64, ncclSum, d->comm, st));
-            pcg_update_kernel<<<g2, PCG_THREADS, 0, st>>>(dev, nloc, Sp, 1, Sq + 1, 1, x_local, p, r, q, dinv,
-                                                         part_rz, part_rr);
+            NODAL_TRY(exchange(u, sx));
+            NODAL_TRY(launch_k1(A, dev, u, w, part_d, sx));
+            cgcg_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, part_g, part_rr, nullptr, g2, part_d, A.g1, nxt, 0);
             KERNEL_CHECK();
-            dist_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, nullptr, g2, Sp + 1);
-            KERNEL_CHECK();
-            NCCL_TRY(g_nccl.AllReduce(Sp + 1, Sp + 1, 2, ncclFloat64, ncclSum, d->comm, st));
-            pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(dev, nloc, Sq + 1, Sp + 1, Sp + 2, 1, p, r, dinv);
-            KERNEL_CHECK();
+            if (R > 1) NCCL_TRY(g_nccl.AllReduce(nxt, nxt, 3, ncclFloat64, ncclSum, d->comm, sx));
             return NODAL_OK;
         };
 
         NODAL_TRY(start(1));
+        const int CH = 32;
+        const bool use_graph = getenv("NODAL_DIST_NO_GRAPH") == nullptr;
+        if (use_graph) {
+            const unsigned long long before = g_nodal_launches;
+            CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+            int crc = NODAL_OK;
+            for (int i = 0; i < CH && crc == NODAL_OK; ++i) crc = iteration(i & 1, cap);
+            cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+            if (crc != NODAL_OK) return crc;
+            CUDA_TRY(ce);
+            CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
+            launches_per_chunk = g_nodal_launches - before;
+            g_nodal_launches = before;
+        }
         CUDA_TRY(cudaEventRecord(ev1, st));
         PcgDev* poll = reinterpret_cast<PcgDev*>(ctx->pinned);
         double last_true_rr = -1.0;
-        const int CH = 32;
         for (;;) {
             const int64_t max_chunks = (int64_t)maxit / CH + 3;
             int64_t k = 0;
             for (;; ++k) {
-                for (int i = 0; i < CH; ++i) NODAL_TRY(iteration(i & 1));
+                if (use_graph) {
+                    CUDA_TRY(cudaGraphLaunch(gexec, st));
+                    g_nodal_launches += launches_per_chunk;
+                } else {
+                    for (int i = 0; i < CH; ++i) NODAL_TRY(iteration(i & 1, st));
+                }
                 CUDA_TRY(cudaMemcpyAsync(&poll[k & 1], dev, sizeof(PcgDev), cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaEventRecord(ev_poll[k & 1], st));
                 if (k >= 1) {
@@ -457,11 +617,13 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             host = poll[k & 1];
             if (!host.done) host.status = NODAL_NOT_CONVERGED;
             if (host.status == NODAL_BREAKDOWN) break;
-            NODAL_TRY(start(0));
+            const int recurrence_status = host.status;
+            const int iters_so_far = host.iters;
+            NODAL_TRY(start(0));     // true residual of the current x (and a restart, if needed)
             CUDA_TRY(cudaMemcpyAsync(&poll[0], dev, sizeof(PcgDev), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            const int recurrence_status = host.status;
             host = poll[0];
+            host.iters = iters_so_far;
             if (host.rr <= host.tol2) { host.status = NODAL_OK; break; }
             if (recurrence_status == NODAL_NOT_CONVERGED || host.iters >= host.maxit) {
                 host.status = NODAL_NOT_CONVERGED;
@@ -496,6 +658,9 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     };
     const int rc = run();
     cudaStreamSynchronize(st);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    if (cap) cudaStreamDestroy(cap);
     if (sell) sell_free(sell);
     for (void* p : owned) cudaFree(p);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);

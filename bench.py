@@ -23,6 +23,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout (one JSON line only)
 
 import numpy as np  # noqa: E402
 
@@ -270,7 +272,8 @@ def run_ours(args):
                    "parallelism": f"rows x{world}" if world > 1 else "single GPU"},
         "time_to_solution_s": ms_per_step * 1e-3, "iterations": iters, "relres": info["relres"],
         "R": r, "R_minus_infinite_grid_limit": r - KNIGHT_LIMIT,
-        "pcg_solve_ms": solve_ms,
+        "pcg_solve_ms": solve_ms, "pcg_setup_ms": info.get("setup_ms"),
+        "dist_breakdown_ms": {k: info[k] for k in ("assemble_wall_ms", "solve_wall_ms", "host_ms", "comm") if k in info},
         "pcg_achieved_gbs": pcg_bytes / (solve_ms * 1e-3) / 1e9 if world == 1 else None,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
         "cpu_baseline": cpu,

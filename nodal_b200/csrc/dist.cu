@@ -21,6 +21,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "pcg_kernels.cuh"
@@ -81,10 +82,38 @@ int load_nccl() {
         }                                                                                    \
     } while (0)
 
+// Symmetric peer-mapped buffer (one per rank, same size everywhere): a 4 KB mailbox followed
+// by the rank's u vector [owned | halo].  Peers write halo entries and reduction operands
+// straight into it over NVLink (CUDA IPC mappings), so the iteration needs no NCCL call.
+constexpr int P2P_MAXR = 8;
+constexpr size_t P2P_HDR = 4096;
+struct P2PMail {
+    double red[2][P2P_MAXR][4];            // [parity][source rank] = {gamma, delta, rr, tag}
+    unsigned long long hflag[P2P_MAXR];    // halo of iteration `tag` from that rank has landed
+    unsigned long long err;
+};
+
 struct nodal_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, device = 0;
+    // peer-memory path
+    bool p2p_disabled = false;
+    char* shm = nullptr;
+    size_t shm_bytes = 0;
+    std::vector<char*> peer;               // host copy of the mapped base pointers (peer[rank] = shm)
+    char** peer_dev = nullptr;             // the same on the device
+    unsigned long long* seq = nullptr;     // device: reductions completed since the buffer was made
 };
+
+static void p2p_release(nodal_dist* d) {
+    for (size_t o = 0; o < d->peer.size(); ++o)
+        if ((int)o != d->rank && d->peer[o]) cudaIpcCloseMemHandle(d->peer[o]);
+    d->peer.clear();
+    if (d->shm) cudaFree(d->shm);
+    if (d->peer_dev) cudaFree(d->peer_dev);
+    if (d->seq) cudaFree(d->seq);
+    d->shm = nullptr; d->peer_dev = nullptr; d->seq = nullptr; d->shm_bytes = 0;
+}
 
 extern "C" int nodal_dist_unique_id(uint8_t* id_h) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
@@ -119,6 +148,8 @@ extern "C" int nodal_dist_create(nodal_ctx* ctx, const uint8_t* id_h, int32_t ra
 extern "C" int nodal_dist_destroy(nodal_dist* d) {
     if (!d) return NODAL_OK;
     cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    p2p_release(d);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     delete d;
     return NODAL_OK;
@@ -336,10 +367,179 @@ __global__ void cgcg_scalars_kernel(PcgDev* dev, double* SC, double rtol, int ma
     else if (!(rr == rr)) { dev->done = 1; dev->status = NODAL_BREAKDOWN; }
 }
 
+// ---------------------------------------------------------------- peer-memory kernels
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr long long P2P_SPIN_LIMIT = 6000000000ll;   // ~3 s of SM clocks, then give up (no hang)
+
+// One CTA: copy the entries every peer needs from my u into the halo tail of THEIR u, then
+// raise my flag in their mailbox.
+__global__ void __launch_bounds__(1024)
+p2p_push_kernel(const PcgDev* __restrict__ dev, const unsigned long long* __restrict__ seq, int R, int me,
+                const int32_t* __restrict__ send_idx, const int32_t* __restrict__ send_off,
+                const long long* __restrict__ dest_off, char* const* __restrict__ peer,
+                const double* __restrict__ u) {
+    if (block_done(&dev->done)) return;
+    const unsigned long long tag = *seq + 1;
+    for (int o = 0; o < R; ++o) {
+        if (o == me) continue;
+        const int b = send_off[o], e = send_off[o + 1];
+        double* dst = reinterpret_cast<double*>(peer[o] + P2P_HDR) + dest_off[o];
+        for (int j = b + threadIdx.x; j < e; j += blockDim.x) dst[j - b] = u[send_idx[j]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < R && threadIdx.x != me && send_off[threadIdx.x + 1] > send_off[threadIdx.x]) {
+        P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
+        __threadfence_system();
+        st_sys_u64(&m->hflag[me], tag);
+    }
+}
+
+// One warp: wait until every neighbour's halo block of this iteration has landed in my u.
+__global__ void p2p_wait_halo_kernel(PcgDev* __restrict__ dev, const unsigned long long* __restrict__ seq, int R,
+                                     int me, const int32_t* __restrict__ need_cnt, P2PMail* mine) {
+    if (*reinterpret_cast<volatile int*>(&dev->done)) return;
+    const unsigned long long tag = *seq + 1;
+    const int o = threadIdx.x;
+    bool timeout = false;
+    if (o < R && o != me && need_cnt[o] > 0) {
+        const long long t0 = clock64();
+        while (ld_sys_u64(&mine->hflag[o]) < tag) {
+            if (clock64() - t0 > P2P_SPIN_LIMIT) { timeout = true; break; }
+        }
+    }
+    if (__any_sync(0xffffffffu, timeout) && threadIdx.x == 0) {
+        dev->done = 1;
+        dev->status = NODAL_CUDA_ERROR;
+        mine->err = 1;
+    }
+    __threadfence_system();
+}
+
+// One CTA: local sums -> every rank's mailbox; wait for all ranks; sum in rank order (the
+// result is bitwise identical everywhere); advance the sequence number.
+__global__ void __launch_bounds__(PCG_THREADS)
+p2p_reduce_kernel(PcgDev* __restrict__ dev, unsigned long long* __restrict__ seq, int R, int me,
+                  const double* __restrict__ part_g, const double* __restrict__ part_rr, int cnt_v,
+                  const double* __restrict__ part_d, int cnt_s, char* const* __restrict__ peer,
+                  double* __restrict__ out) {
+    __shared__ double sm[40];
+    __shared__ int s_timeout;
+    if (block_done(&dev->done)) return;
+    const double g = reduce_partials(part_g, cnt_v, sm);
+    const double rr = reduce_partials(part_rr, cnt_v, sm);
+    const double dl = reduce_partials(part_d, cnt_s, sm);
+    const unsigned long long s0 = *seq;
+    const unsigned long long tag = s0 + 1;
+    const int par = (int)(s0 & 1ull);
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    if (threadIdx.x < R) {
+        P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
+        volatile double* slot = m->red[par][me];
+        slot[0] = g; slot[1] = dl; slot[2] = rr;
+        __threadfence_system();
+        st_sys_u64(reinterpret_cast<unsigned long long*>(&m->red[par][me][3]), tag);
+    }
+    P2PMail* mine = reinterpret_cast<P2PMail*>(peer[me]);
+    if (threadIdx.x < R) {
+        const unsigned long long* tp = reinterpret_cast<const unsigned long long*>(&mine->red[par][threadIdx.x][3]);
+        const long long t0 = clock64();
+        while (ld_sys_u64(tp) != tag) {
+            if (clock64() - t0 > P2P_SPIN_LIMIT) { s_timeout = 1; break; }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_timeout) {
+            dev->done = 1; dev->status = NODAL_CUDA_ERROR; mine->err = 1;
+        } else {
+            double sg = 0.0, sd = 0.0, sr = 0.0;
+            for (int t = 0; t < R; ++t) {
+                const volatile double* slot = mine->red[par][t];
+                sg += slot[0]; sd += slot[1]; sr += slot[2];
+            }
+            out[0] = sg; out[1] = sd; out[2] = sr;
+            *seq = tag;
+            if (dev->iters >= dev->maxit) { dev->done = 1; dev->status = NODAL_NOT_CONVERGED; }
+        }
+    }
+}
+
 static int grid_of(nodal_ctx* ctx, int64_t work) {
     int64_t b = (work + DT - 1) / DT;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
     return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+
+// Collective: make sure every rank owns a peer-mapped buffer of at least `bytes`.
+// Returns NODAL_OK and sets *usable; any failure on any rank disables the path everywhere.
+static int p2p_ensure(nodal_ctx* ctx, nodal_dist* d, size_t bytes, cudaStream_t st, bool* usable) {
+    *usable = false;
+    const int R = d->nranks, me = d->rank;
+    if (R < 2 || R > P2P_MAXR || d->p2p_disabled || getenv("NODAL_DIST_NO_P2P")) return NODAL_OK;
+    int* flag_dev = nullptr;
+    CUDA_TRY(cudaMalloc(&flag_dev, 256));
+    int ok = 1;
+    if (d->shm_bytes < bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        p2p_release(d);
+        const size_t want = align_up(bytes + bytes / 4, 2 << 20);
+        cudaIpcMemHandle_t mine;
+        char* handles_dev = nullptr;
+        std::vector<cudaIpcMemHandle_t> all((size_t)R);
+        if (cudaMalloc(&d->shm, want) != cudaSuccess) ok = 0;
+        if (ok && cudaMemset(d->shm, 0, P2P_HDR) != cudaSuccess) ok = 0;
+        if (ok && cudaIpcGetMemHandle(&mine, d->shm) != cudaSuccess) ok = 0;
+        if (!ok) memset(&mine, 0, sizeof(mine));
+        (void)cudaGetLastError();
+        CUDA_TRY(cudaMalloc(&handles_dev, sizeof(cudaIpcMemHandle_t) * (size_t)(R + 1)));
+        CUDA_TRY(cudaMemcpy(handles_dev + sizeof(cudaIpcMemHandle_t) * (size_t)R, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        NCCL_TRY(g_nccl.AllGather(handles_dev + sizeof(cudaIpcMemHandle_t) * (size_t)R, handles_dev,
+                                  sizeof(cudaIpcMemHandle_t), ncclChar, d->comm, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(all.data(), handles_dev, sizeof(cudaIpcMemHandle_t) * (size_t)R, cudaMemcpyDeviceToHost));
+        cudaFree(handles_dev);
+        d->peer.assign((size_t)R, nullptr);
+        for (int o = 0; o < R && ok; ++o) {
+            if (o == me) { d->peer[o] = d->shm; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[o], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = 0;
+                (void)cudaGetLastError();
+            }
+            d->peer[o] = static_cast<char*>(ptr);
+        }
+        if (ok) {
+            if (cudaMalloc(&d->peer_dev, sizeof(char*) * P2P_MAXR) != cudaSuccess ||
+                cudaMemcpy(d->peer_dev, d->peer.data(), sizeof(char*) * (size_t)R, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMalloc(&d->seq, 256) != cudaSuccess || cudaMemset(d->seq, 0, 256) != cudaSuccess)
+                ok = 0;
+        }
+        if (ok) d->shm_bytes = want;
+    }
+    // agree on the outcome (also a barrier: nobody writes a mailbox before it has been zeroed)
+    CUDA_TRY(cudaMemcpy(flag_dev, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllReduce(flag_dev, flag_dev, 1, ncclInt32, ncclMin, d->comm, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int all_ok = 0;
+    CUDA_TRY(cudaMemcpy(&all_ok, flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(flag_dev);
+    if (!all_ok) {
+        p2p_release(d);
+        d->p2p_disabled = true;
+        return NODAL_OK;
+    }
+    *usable = true;
+    return NODAL_OK;
 }
 
 extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, const int32_t* bounds_h,
@@ -382,6 +582,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     cudaGraphExec_t gexec = nullptr;
     cudaStream_t cap = nullptr;
     unsigned long long launches_per_chunk = 0;
+    double host_ms_capture = 0.0;
+    bool used_p2p = false;
 
     auto run = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ev0, st));
@@ -455,13 +657,23 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             }
             for (int o2 = 0; o2 < R; ++o2) need_off[o2 + 1] = need_off[o2] + need_from[o2];
         }
-        int32_t* cnt_dev = static_cast<int32_t*>(dmalloc(sizeof(int32_t) * (size_t)R * (R + 1)));
+        const int W = R + 1;   // per rank: R counts + its u length
+        int32_t* cnt_dev = static_cast<int32_t*>(dmalloc(sizeof(int32_t) * (size_t)W * (R + 1)));
         if (!cnt_dev) return NODAL_CUDA_ERROR;
-        CUDA_TRY(cudaMemcpyAsync(cnt_dev + (size_t)R * R, need_from.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, st));
-        NCCL_TRY(g_nccl.AllGather(cnt_dev + (size_t)R * R, cnt_dev, R, ncclInt32, d->comm, st));
-        std::vector<int32_t> cnt((size_t)R * R);
-        CUDA_TRY(cudaMemcpyAsync(cnt.data(), cnt_dev, sizeof(int32_t) * (size_t)R * R, cudaMemcpyDeviceToHost, st));
+        std::vector<int32_t> mine_row(W, 0);
+        for (int o = 0; o < R; ++o) mine_row[o] = need_from[o];
+        mine_row[R] = (int32_t)((nloc + nhalo + 2 + 255) / 256);      // u length in units of 256 doubles
+        CUDA_TRY(cudaMemcpyAsync(cnt_dev + (size_t)W * R, mine_row.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
+        NCCL_TRY(g_nccl.AllGather(cnt_dev + (size_t)W * R, cnt_dev, W, ncclInt32, d->comm, st));
+        std::vector<int32_t> gathered((size_t)W * R);
+        CUDA_TRY(cudaMemcpyAsync(gathered.data(), cnt_dev, sizeof(int32_t) * (size_t)W * R, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<int32_t> cnt((size_t)R * R);
+        int64_t max_units = 0;
+        for (int s2 = 0; s2 < R; ++s2) {
+            for (int o = 0; o < R; ++o) cnt[(size_t)s2 * R + o] = gathered[(size_t)s2 * W + o];
+            max_units = std::max<int64_t>(max_units, gathered[(size_t)s2 * W + R]);
+        }
         // cnt[s*R + o] = entries rank s needs from owner o
         std::vector<int32_t> send_cnt(R, 0), send_off(R + 1, 0);
         for (int s = 0; s < R; ++s) send_cnt[s] = cnt[(size_t)s * R + me];
@@ -481,6 +693,29 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             dist_rebase_kernel<<<grid_of(ctx, send_total), DT, 0, st>>>(send_total, send_idx, rb);
             KERNEL_CHECK();
         }
+        // ---------------- peer-memory path: symmetric buffer + push metadata ----------------
+        bool p2p = false;
+        NODAL_TRY(p2p_ensure(ctx, d, P2P_HDR + (size_t)max_units * 256 * sizeof(double), st, &p2p));
+        int32_t* send_off_dev = nullptr;
+        int32_t* need_cnt_dev = nullptr;
+        long long* dest_off_dev = nullptr;
+        if (p2p) {
+            std::vector<long long> dest_off(R, 0);
+            for (int o = 0; o < R; ++o) {
+                long long off = bounds_h[o + 1] - bounds_h[o];            // peer's owned part
+                for (int o2 = 0; o2 < me; ++o2) off += cnt[(size_t)o * R + o2];   // blocks of lower-ranked owners
+                dest_off[o] = off;
+            }
+            send_off_dev = static_cast<int32_t*>(dmalloc(sizeof(int32_t) * (size_t)(R + 1)));
+            need_cnt_dev = static_cast<int32_t*>(dmalloc(sizeof(int32_t) * (size_t)R));
+            dest_off_dev = static_cast<long long*>(dmalloc(sizeof(long long) * (size_t)R));
+            if (!send_off_dev || !need_cnt_dev || !dest_off_dev) return NODAL_CUDA_ERROR;
+            CUDA_TRY(cudaMemcpyAsync(send_off_dev, send_off.data(), sizeof(int32_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(need_cnt_dev, need_from.data(), sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(dest_off_dev, dest_off.data(), sizeof(long long) * (size_t)R, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+        }
+        used_p2p = p2p;
         // ---------------- local operator in the solver-private layout ----------------
         NODAL_TRY(sell_from_csr(ctx, nloc, nnz, indptr, lcols, data, &sell, st));   // resets the arena
         Mat A;
@@ -507,7 +742,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         double* p = carve<double>(ctx, nloc);
         double* s = carve<double>(ctx, nloc);                           // s = A p (recurrence)
         double* w = carve<double>(ctx, nloc);                           // w = A u
-        double* u = carve<double>(ctx, (size_t)nloc + nhalo + 2);       // u = D^-1 r, [owned | halo]
+        double* u = p2p ? reinterpret_cast<double*>(d->shm + P2P_HDR)   // u = D^-1 r, [owned | halo]
+                        : carve<double>(ctx, (size_t)nloc + nhalo + 2);
         double* xe = carve<double>(ctx, (size_t)nloc + nhalo + 2);      // x in the same layout
         double* part_g = carve<double>(ctx, gmax);
         double* part_d = carve<double>(ctx, gmax);
@@ -568,11 +804,26 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
                                                           part_g, part_rr);
             KERNEL_CHECK();
-            NODAL_TRY(exchange(u, sx));
+            if (p2p) {
+                p2p_push_kernel<<<1, 1024, 0, sx>>>(dev, d->seq, R, me, send_idx, send_off_dev, dest_off_dev,
+                                                    d->peer_dev, u);
+                KERNEL_CHECK();
+                p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
+                                                       reinterpret_cast<P2PMail*>(d->shm));
+                KERNEL_CHECK();
+            } else {
+                NODAL_TRY(exchange(u, sx));
+            }
             NODAL_TRY(launch_k1(A, dev, u, w, part_d, sx));
-            cgcg_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, part_g, part_rr, nullptr, g2, part_d, A.g1, nxt, 0);
-            KERNEL_CHECK();
-            if (R > 1) NCCL_TRY(g_nccl.AllReduce(nxt, nxt, 3, ncclFloat64, ncclSum, d->comm, sx));
+            if (p2p) {
+                p2p_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, d->seq, R, me, part_g, part_rr, g2, part_d, A.g1,
+                                                            d->peer_dev, nxt);
+                KERNEL_CHECK();
+            } else {
+                cgcg_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, part_g, part_rr, nullptr, g2, part_d, A.g1, nxt, 0);
+                KERNEL_CHECK();
+                if (R > 1) NCCL_TRY(g_nccl.AllReduce(nxt, nxt, 3, ncclFloat64, ncclSum, d->comm, sx));
+            }
             return NODAL_OK;
         };
 
@@ -580,6 +831,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         const int CH = 32;
         const bool use_graph = getenv("NODAL_DIST_NO_GRAPH") == nullptr;
         if (use_graph) {
+            const auto c0 = std::chrono::steady_clock::now();
             const unsigned long long before = g_nodal_launches;
             CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
@@ -591,6 +843,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
             launches_per_chunk = g_nodal_launches - before;
             g_nodal_launches = before;
+            host_ms_capture = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
         }
         CUDA_TRY(cudaEventRecord(ev1, st));
         PcgDev* poll = reinterpret_cast<PcgDev*>(ctx->pinned);
@@ -653,17 +906,29 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             stats_h[7] = A.g1;
             stats_h[12] = (double)halo_total;
             stats_h[13] = (double)send_total;
+            stats_h[9] = used_p2p ? 1.0 : 0.0;
         }
         return host.status;
     };
+    const auto h0 = std::chrono::steady_clock::now();
     const int rc = run();
     cudaStreamSynchronize(st);
+    const auto h1 = std::chrono::steady_clock::now();
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
     if (cap) cudaStreamDestroy(cap);
+    const auto h2 = std::chrono::steady_clock::now();
     if (sell) sell_free(sell);
     for (void* p : owned) cudaFree(p);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
     cudaEventDestroy(ev_poll[0]); cudaEventDestroy(ev_poll[1]);
+    const auto h3 = std::chrono::steady_clock::now();
+    if (stats_h) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        stats_h[14] = ms(h0, h1);       // host wall of setup + solve
+        stats_h[15] = ms(h1, h2);       // graph teardown
+        stats_h[11] = ms(h2, h3);       // buffer teardown
+        stats_h[10] = host_ms_capture;  // graph capture + instantiate
+    }
     return rc;
 }

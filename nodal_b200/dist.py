@@ -103,7 +103,10 @@ class DistPCG:
         info = dict(solver="dist_pcg", status=st, iterations=iters.value, relres=relres.value,
                     restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4],
                     format="sell32" if stats[5] else "csr", stored_nnz=int(stats[6]),
-                    halo_recv=int(stats[12]), halo_send=int(stats[13]), nnz=int(data.numel()))
+                    halo_recv=int(stats[12]), halo_send=int(stats[13]), nnz=int(data.numel()),
+                    comm="p2p" if stats[9] else "nccl",
+                    host_ms=dict(run=stats[14], graph_teardown=stats[15], buffer_teardown=stats[11],
+                                 graph_capture=stats[10]))
         return x, info
 
 
@@ -122,10 +125,17 @@ class GridRunner:
         self.dtab = dev.upload_table(self.local)
 
     def step(self, _unused=None):
+        import time
         import torch.distributed as dist
         torch = self.dev.torch
+        t0 = time.perf_counter()
         indptr, indices, data, rhs = self.pcg.assemble_local(self.local, self.bounds, dtab=self.dtab)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         x, info = self.pcg.solve(self.n, self.bounds, indptr, indices, data, rhs, rtol=self.rtol)
+        t2 = time.perf_counter()
+        info["assemble_wall_ms"] = (t1 - t0) * 1e3
+        info["solve_wall_ms"] = (t2 - t1) * 1e3
         r = torch.zeros(1, dtype=torch.float64, device=self.dev.dev)
         if self.rank == self.owner:
             r[0] = x[self.probe_row - int(self.bounds[self.rank])]

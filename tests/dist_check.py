@@ -40,7 +40,7 @@ def main():
         r, info = runner.step()
         x_loc, _ = None, None
         msg = dict(N=N, world=world, R=r, iterations=info["iterations"], relres=info["relres"],
-                   status=info["status"], halo_recv=info["halo_recv"], solve_ms=info["solve_ms"])
+                   status=info["status"], halo_recv=info["halo_recv"], solve_ms=info["solve_ms"], comm=info["comm"])
         if N in GOLD:
             msg["rel_err_vs_reference"] = abs(r - GOLD[N]) / GOLD[N]
             ok &= msg["rel_err_vs_reference"] < 1e-9

@@ -474,6 +474,219 @@ p2p_reduce_kernel(PcgDev* __restrict__ dev, unsigned long long* __restrict__ seq
     }
 }
 
+// ---------------------------------------------------------------- fused peer-memory iteration
+// Two kernels per iteration.  The vector pass ends with the halo push (done by whichever CTA
+// finishes last); the SpMV starts by waiting for the neighbours' pushes and ends with the
+// mailbox all-reduce (again the last CTA).  Reduction order is fixed, so the result does not
+// depend on which CTA happens to be last.
+struct DistSync {
+    unsigned int ticket_v, ticket_s;
+};
+
+__device__ __forceinline__ double reduce_partials_cg(const double* part, int count, double* smem) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) t += __ldcg(&part[i]);
+    return block_sum(t, smem);
+}
+
+__global__ void __launch_bounds__(PCG_THREADS)
+dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur, const double* __restrict__ prev,
+                        double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                        double* __restrict__ s, const double* __restrict__ w, const double* __restrict__ dinv,
+                        double* u, double* __restrict__ part_g, double* __restrict__ part_rr,
+                        DistSync* sy, const unsigned long long* __restrict__ seq, int R, int me,
+                        const int32_t* __restrict__ send_idx, const int32_t* __restrict__ send_off,
+                        const long long* __restrict__ dest_off, char* const* __restrict__ peer) {
+    __shared__ double sm[40];
+    __shared__ int s_last;
+    if (block_done(&dev->done)) return;
+    const double g = cur[0], dl = cur[1], rr = cur[2];
+    const double gp = prev[0], ap = prev[3];
+    const bool conv = rr <= dev->tol2;
+    double beta = 0.0, den = dl;
+    if (ap != 0.0) { beta = g / gp; den = dl - beta * g / ap; }
+    const double alpha = g / den;
+    const bool bad = !(den > 0.0) || !(rr == rr);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dev->rr = rr;
+        if (conv) { dev->done = 1; dev->status = NODAL_OK; }
+        else if (bad) { dev->done = 1; dev->status = NODAL_BREAKDOWN; }
+        else { dev->iters = dev->iters + 1; cur[3] = alpha; }
+    }
+    if (conv || bad) return;
+    double lg = 0.0, lrr = 0.0;
+    const int64_t n2 = n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* s2 = reinterpret_cast<double2*>(s);
+    double2* u2 = reinterpret_cast<double2*>(u);
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 xv = x2[i], rv = r2[i], pv = p2[i], sv = s2[i];
+        const double2 wv = w2[i], dv = d2[i];
+        pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
+        sv.x = fma(beta, sv.x, wv.x);        sv.y = fma(beta, sv.y, wv.y);
+        xv.x = fma(alpha, pv.x, xv.x);       xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, sv.x, rv.x);      rv.y = fma(-alpha, sv.y, rv.y);
+        double2 uv;
+        uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
+        p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
+        lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+        lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const double pv = fma(beta, p[i], dinv[i] * r[i]);
+        const double sv = fma(beta, s[i], w[i]);
+        const double rv = fma(-alpha, sv, r[i]);
+        const double uv = dinv[i] * rv;
+        p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
+        lg = fma(rv, uv, lg);
+        lrr = fma(rv, rv, lrr);
+    }
+    lg = block_sum(lg, sm);
+    lrr = block_sum(lrr, sm);
+    if (threadIdx.x == 0) { part_g[blockIdx.x] = lg; part_rr[blockIdx.x] = lrr; }
+    // ---- the CTA that finishes last pushes the boundary entries to the peers
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&sy->ticket_v, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) sy->ticket_v = 0;
+    __threadfence();
+    const unsigned long long tag = *seq + 1;
+    for (int o = 0; o < R; ++o) {
+        if (o == me) continue;
+        const int b = send_off[o], e = send_off[o + 1];
+        double* dst = reinterpret_cast<double*>(peer[o] + P2P_HDR) + dest_off[o];
+        for (int j = b + threadIdx.x; j < e; j += blockDim.x) dst[j - b] = __ldcg(&u[send_idx[j]]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < R && threadIdx.x != me && send_off[threadIdx.x + 1] > send_off[threadIdx.x]) {
+        P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
+        __threadfence_system();
+        st_sys_u64(&m->hflag[me], tag);
+    }
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 4)
+dist_spmv_allreduce_sell_kernel(PcgDev* __restrict__ dev, int32_t n, int32_t nslices,
+                                const u32* __restrict__ slice_w, const int32_t* __restrict__ cols,
+                                const double* __restrict__ vals, const double* __restrict__ u,
+                                double* __restrict__ w, double* part_d, const double* __restrict__ part_g,
+                                const double* __restrict__ part_rr, int cnt_v, DistSync* sy,
+                                unsigned long long* seq, int R, int me, const int32_t* __restrict__ need_cnt,
+                                char* const* __restrict__ peer, double* __restrict__ out) {
+    __shared__ double sm[40];
+    __shared__ int s_flag;
+    if (block_done(&dev->done)) return;
+    const unsigned long long s0 = *seq;
+    const unsigned long long tag = s0 + 1;
+    P2PMail* mine = reinterpret_cast<P2PMail*>(peer[me]);
+    // ---- wait for the neighbours' halo entries of this iteration
+    if (threadIdx.x == 0) s_flag = 0;
+    __syncthreads();
+    if (threadIdx.x < R && threadIdx.x != me && need_cnt[threadIdx.x] > 0) {
+        const long long t0 = clock64();
+        while (ld_sys_u64(&mine->hflag[threadIdx.x]) < tag) {
+            if (clock64() - t0 > P2P_SPIN_LIMIT) { s_flag = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_flag) {
+        if (threadIdx.x == 0) { dev->done = 1; dev->status = NODAL_CUDA_ERROR; mine->err = 1; }
+        return;
+    }
+    // ---- w = A u, partial sums of w.u
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int64_t s = warp; s < nslices; s += nwarps) {
+        const u32 w0 = slice_w[s];
+        const int wd = (int)(slice_w[s + 1] - w0);
+        const int64_t base = (int64_t)w0 * 32 + lane;
+        double acc = 0.0;
+        for (int k = 0; k < wd; k += 8) {
+            int32_t c[8];
+            double v[8], xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (k + i < wd) {
+                    c[i] = cols[base + (int64_t)(k + i) * 32];
+                    v[i] = vals[base + (int64_t)(k + i) * 32];
+                }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (k + i < wd) xv[i] = __ldg(&u[c[i]]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (k + i < wd) acc = fma(v[i], xv[i], acc);
+        }
+        const int64_t row = s * 32 + lane;
+        if (row < n) {
+            w[row] = acc;
+            dot = fma(acc, __ldg(&u[row]), dot);
+        }
+    }
+    dot = block_sum(dot, sm);
+    if (threadIdx.x == 0) part_d[blockIdx.x] = dot;
+    // ---- the CTA that finishes last runs the all-reduce through the peers' mailboxes
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&sy->ticket_s, 1u);
+        s_flag = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    if (threadIdx.x == 0) sy->ticket_s = 0;
+    __threadfence();
+    const double g = reduce_partials_cg(part_g, cnt_v, sm);
+    const double rr = reduce_partials_cg(part_rr, cnt_v, sm);
+    const double dl = reduce_partials_cg(part_d, (int)gridDim.x, sm);
+    const int par = (int)(s0 & 1ull);
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = 0;
+    __syncthreads();
+    if (threadIdx.x < R) {
+        P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
+        volatile double* slot = m->red[par][me];
+        slot[0] = g; slot[1] = dl; slot[2] = rr;
+        __threadfence_system();
+        st_sys_u64(reinterpret_cast<unsigned long long*>(&m->red[par][me][3]), tag);
+        const unsigned long long* tp = reinterpret_cast<const unsigned long long*>(&mine->red[par][threadIdx.x][3]);
+        const long long t0 = clock64();
+        while (ld_sys_u64(tp) != tag) {
+            if (clock64() - t0 > P2P_SPIN_LIMIT) { s_flag = 1; break; }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_flag) {
+            dev->done = 1; dev->status = NODAL_CUDA_ERROR; mine->err = 1;
+        } else {
+            double sg = 0.0, sd = 0.0, sr = 0.0;
+            for (int t = 0; t < R; ++t) {
+                const volatile double* slot = mine->red[par][t];
+                sg += slot[0]; sd += slot[1]; sr += slot[2];
+            }
+            out[0] = sg; out[1] = sd; out[2] = sr;
+            *seq = tag;
+            if (dev->iters >= dev->maxit) { dev->done = 1; dev->status = NODAL_NOT_CONVERGED; }
+        }
+    }
+}
+
 static int grid_of(nodal_ctx* ctx, int64_t work) {
     int64_t b = (work + DT - 1) / DT;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -716,6 +929,9 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
         }
         used_p2p = p2p;
+        DistSync* sy = static_cast<DistSync*>(dmalloc(256));
+        if (!sy) return NODAL_CUDA_ERROR;
+        CUDA_TRY(cudaMemsetAsync(sy, 0, 256, st));
         // ---------------- local operator in the solver-private layout ----------------
         NODAL_TRY(sell_from_csr(ctx, nloc, nnz, indptr, lcols, data, &sell, st));   // resets the arena
         Mat A;
@@ -733,6 +949,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             const int64_t want = ((int64_t)nloc * A.tpr + PCG_THREADS - 1) / PCG_THREADS;
             A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8, want);
         }
+        const bool fused = p2p && A.sell && getenv("NODAL_DIST_NO_FUSE") == nullptr;
         const int gmax = std::max(A.g1, g2);
         const size_t vloc = align_up(sizeof(double) * (size_t)nloc, 256);
         const size_t vext = align_up(sizeof(double) * (size_t)(nloc + nhalo + 2), 256);
@@ -801,6 +1018,17 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         auto iteration = [&](int par, cudaStream_t sx) -> int {
             double* cur = SC + par * 4;
             double* nxt = SC + (par ^ 1) * 4;
+            if (fused) {
+                dist_vector_push_kernel<<<g2, PCG_THREADS, 0, sx>>>(
+                    dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
+                    send_idx, send_off_dev, dest_off_dev, d->peer_dev);
+                KERNEL_CHECK();
+                dist_spmv_allreduce_sell_kernel<<<A.g1, PCG_THREADS, 0, sx>>>(
+                    dev, nloc, sell->nslices, sell->slice_w, sell->cols, sell->vals, u, w, part_d, part_g,
+                    part_rr, g2, sy, d->seq, R, me, need_cnt_dev, d->peer_dev, nxt);
+                KERNEL_CHECK();
+                return NODAL_OK;
+            }
             cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
                                                           part_g, part_rr);
             KERNEL_CHECK();
@@ -906,7 +1134,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             stats_h[7] = A.g1;
             stats_h[12] = (double)halo_total;
             stats_h[13] = (double)send_total;
-            stats_h[9] = used_p2p ? 1.0 : 0.0;
+            stats_h[9] = used_p2p ? (fused ? 2.0 : 1.0) : 0.0;
         }
         return host.status;
     };

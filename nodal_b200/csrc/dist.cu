@@ -480,15 +480,61 @@ p2p_reduce_kernel(PcgDev* __restrict__ dev, unsigned long long* __restrict__ seq
 // mailbox all-reduce (again the last CTA).  Reduction order is fixed, so the result does not
 // depend on which CTA happens to be last.
 struct DistSync {
-    unsigned int ticket_v, ticket_s;
+    unsigned int ticket_v[64], ticket_s[64];   // [0] = top level, [1 + g] = group g of 32 CTAs
+    unsigned long long dbg[16];                // ns accumulated in the tails (diagnostics)
 };
-
-__device__ __forceinline__ double reduce_partials_cg(const double* part, int count, double* smem) {
-    double t = 0.0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) t += __ldcg(&part[i]);
-    return block_sum(t, smem);
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
+// "Am I the last CTA of the grid to get here?"  Two-level ticket so that no address sees more
+// than ~37 arrivals (a single counter serialises ~1200 same-address atomics, 10+ us).
+__device__ __forceinline__ bool last_cta_arrive(unsigned int* tickets, int* s_flag) {
+    __syncthreads();          // the CTA's writes are ordered before thread 0 ...
+    if (threadIdx.x == 0) {
+        __threadfence();      // ... whose (cumulative) fence publishes them before the ticket
+        const unsigned int g = blockIdx.x >> 5, ngroups = (gridDim.x + 31) >> 5;
+        const unsigned int gsize = min(32u, gridDim.x - g * 32);
+        int last = 0;
+        if (atomicAdd(&tickets[1 + g], 1u) == gsize - 1) {
+            tickets[1 + g] = 0;
+            __threadfence();
+            if (atomicAdd(&tickets[0], 1u) == ngroups - 1) { tickets[0] = 0; last = 1; }
+        }
+        *s_flag = last;
+    }
+    __syncthreads();
+    if (*s_flag) __threadfence();
+    return *s_flag != 0;
+}
+
+// Sum of up to 3 partial arrays (counts <= 8 * blockDim) with all loads in flight at once.
+__device__ __forceinline__ void reduce3_cg(const double* a, int na, const double* b, int nb, const double* c,
+                                           int nc, double* smem, double& sa, double& sb, double& sc) {
+    double va[8], vb[8], vc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = threadIdx.x + k * blockDim.x;
+        va[k] = i < na ? __ldcg(&a[i]) : 0.0;
+        vb[k] = i < nb ? __ldcg(&b[i]) : 0.0;
+        vc[k] = i < nc ? __ldcg(&c[i]) : 0.0;
+    }
+    double ta = 0.0, tb = 0.0, tc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ta += va[k]; tb += vb[k]; tc += vc[k]; }
+    sa = block_sum(ta, smem);
+    sb = block_sum(tb, smem);
+    sc = block_sum(tc, smem);
+}
+
+// Vector pass of the fused iteration.  The first `nbc` CTAs start with the boundary rows (the
+// rows some peer needs): update them, store the new u entries straight into the peers' halo
+// tails, and the last of them to finish raises this rank's flag in the peers' mailboxes and
+// waits for theirs -- so the halo exchange runs under the bulk of the kernel, and the kernel
+// cannot complete before this rank's halo is valid.  Then every CTA does its share of the
+// regular grid-stride update, skipping the boundary rows (bmask).
 __global__ void __launch_bounds__(PCG_THREADS)
 dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur, const double* __restrict__ prev,
                         double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
@@ -496,10 +542,17 @@ dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict_
                         double* u, double* __restrict__ part_g, double* __restrict__ part_rr,
                         DistSync* sy, const unsigned long long* __restrict__ seq, int R, int me,
                         const int32_t* __restrict__ send_idx, const int32_t* __restrict__ send_off,
-                        const long long* __restrict__ dest_off, char* const* __restrict__ peer) {
+                        const long long* __restrict__ dest_off, const int32_t* __restrict__ need_cnt,
+                        const int32_t* __restrict__ blist, int nb, int nbc, const int32_t* __restrict__ push_rng,
+                        const unsigned char* __restrict__ bmask, char* const* __restrict__ peer) {
     __shared__ double sm[40];
     __shared__ int s_last;
     if (block_done(&dev->done)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long now = gtime();
+        if (sy->dbg[10]) { sy->dbg[11] += now - sy->dbg[10]; }   // end of previous S tail -> this V start
+        sy->dbg[8] = now;
+    }
     const double g = cur[0], dl = cur[1], rr = cur[2];
     const double gp = prev[0], ap = prev[3];
     const bool conv = rr <= dev->tol2;
@@ -515,97 +568,149 @@ dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict_
     }
     if (conv || bad) return;
     double lg = 0.0, lrr = 0.0;
-    const int64_t n2 = n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    double2* x2 = reinterpret_cast<double2*>(x);
-    double2* r2 = reinterpret_cast<double2*>(r);
-    double2* p2 = reinterpret_cast<double2*>(p);
-    double2* s2 = reinterpret_cast<double2*>(s);
-    double2* u2 = reinterpret_cast<double2*>(u);
-    const double2* w2 = reinterpret_cast<const double2*>(w);
-    const double2* d2 = reinterpret_cast<const double2*>(dinv);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-        double2 xv = x2[i], rv = r2[i], pv = p2[i], sv = s2[i];
-        const double2 wv = w2[i], dv = d2[i];
-        pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
-        sv.x = fma(beta, sv.x, wv.x);        sv.y = fma(beta, sv.y, wv.y);
-        xv.x = fma(alpha, pv.x, xv.x);       xv.y = fma(alpha, pv.y, xv.y);
-        rv.x = fma(-alpha, sv.x, rv.x);      rv.y = fma(-alpha, sv.y, rv.y);
-        double2 uv;
-        uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
-        p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
-        lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
-        lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
+    if ((int)blockIdx.x < nbc) {
+        // ---------------- boundary rows first ----------------
+        const unsigned long long tv0 = gtime();
+        const int chunk = (nb + nbc - 1) / nbc;
+        const int k0 = blockIdx.x * chunk, k1 = min(nb, k0 + chunk);
+        for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+            const int i = blist[k];
+            const double pv = fma(beta, p[i], dinv[i] * r[i]);
+            const double sv = fma(beta, s[i], w[i]);
+            const double rv = fma(-alpha, sv, r[i]);
+            const double uv = dinv[i] * rv;
+            p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
+            lg = fma(rv, uv, lg);
+            lrr = fma(rv, rv, lrr);
+        }
+        __syncthreads();
+        // entries of the (sorted) send lists that reference my rows: ranges precomputed on the host
+        for (int o = 0; o < R; ++o) {
+            if (o == me) continue;
+            const int b = send_off[o];
+            const int first = push_rng[(blockIdx.x * R + o) * 2], last = push_rng[(blockIdx.x * R + o) * 2 + 1];
+            double* dst = reinterpret_cast<double*>(peer[o] + P2P_HDR) + dest_off[o];
+            for (int j = first + threadIdx.x; j < last; j += blockDim.x) dst[j - b] = u[send_idx[j]];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();   // cumulative: covers the whole CTA's local and remote stores
+            const unsigned int t = atomicAdd(&sy->ticket_v[0], 1u);
+            s_last = (t == (unsigned int)nbc - 1);
+            if (s_last) sy->ticket_v[0] = 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence_system();
+            const unsigned long long tv1 = gtime();
+            const unsigned long long tag = *seq + 1;
+            P2PMail* mine = reinterpret_cast<P2PMail*>(peer[me]);
+            if (threadIdx.x < R && threadIdx.x != me) {
+                if (send_off[threadIdx.x + 1] > send_off[threadIdx.x]) {
+                    P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
+                    st_sys_u64(&m->hflag[me], tag);
+                }
+                if (need_cnt[threadIdx.x] > 0) {
+                    const long long t0 = clock64();
+                    while (ld_sys_u64(&mine->hflag[threadIdx.x]) < tag) {
+                        if (clock64() - t0 > P2P_SPIN_LIMIT) {
+                            dev->done = 1; dev->status = NODAL_CUDA_ERROR; mine->err = 1;
+                            break;
+                        }
+                    }
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned long long tv2 = gtime();
+                sy->dbg[0] += tv1 - tv0; sy->dbg[1] += tv2 - tv1; sy->dbg[2] += 1;
+            }
+        }
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const int64_t i = n - 1;
-        const double pv = fma(beta, p[i], dinv[i] * r[i]);
-        const double sv = fma(beta, s[i], w[i]);
-        const double rv = fma(-alpha, sv, r[i]);
-        const double uv = dinv[i] * rv;
-        p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
-        lg = fma(rv, uv, lg);
-        lrr = fma(rv, rv, lrr);
+    {
+        // ---------------- regular grid-stride share ----------------
+        const int64_t n2 = n >> 1;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        double2* x2 = reinterpret_cast<double2*>(x);
+        double2* r2 = reinterpret_cast<double2*>(r);
+        double2* p2 = reinterpret_cast<double2*>(p);
+        double2* s2 = reinterpret_cast<double2*>(s);
+        double2* u2 = reinterpret_cast<double2*>(u);
+        const double2* w2 = reinterpret_cast<const double2*>(w);
+        const double2* d2 = reinterpret_cast<const double2*>(dinv);
+        const uchar2* m2 = reinterpret_cast<const uchar2*>(bmask);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+            const uchar2 mk = m2[i];
+            double2 xv = x2[i], rv = r2[i], pv = p2[i], sv = s2[i];
+            const double2 wv = w2[i], dv = d2[i];
+            if (mk.x | mk.y) {   // a boundary row in this pair: element-wise, skipping the rows done above
+                if (!mk.x) {
+                    pv.x = fma(beta, pv.x, dv.x * rv.x); sv.x = fma(beta, sv.x, wv.x);
+                    xv.x = fma(alpha, pv.x, xv.x); rv.x = fma(-alpha, sv.x, rv.x);
+                    const double uv = dv.x * rv.x;
+                    p[2 * i] = pv.x; s[2 * i] = sv.x; x[2 * i] = xv.x; r[2 * i] = rv.x; u[2 * i] = uv;
+                    lg = fma(rv.x, uv, lg); lrr = fma(rv.x, rv.x, lrr);
+                }
+                if (!mk.y) {
+                    pv.y = fma(beta, pv.y, dv.y * rv.y); sv.y = fma(beta, sv.y, wv.y);
+                    xv.y = fma(alpha, pv.y, xv.y); rv.y = fma(-alpha, sv.y, rv.y);
+                    const double uv = dv.y * rv.y;
+                    p[2 * i + 1] = pv.y; s[2 * i + 1] = sv.y; x[2 * i + 1] = xv.y; r[2 * i + 1] = rv.y;
+                    u[2 * i + 1] = uv;
+                    lg = fma(rv.y, uv, lg); lrr = fma(rv.y, rv.y, lrr);
+                }
+                continue;
+            }
+            pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
+            sv.x = fma(beta, sv.x, wv.x);        sv.y = fma(beta, sv.y, wv.y);
+            xv.x = fma(alpha, pv.x, xv.x);       xv.y = fma(alpha, pv.y, xv.y);
+            rv.x = fma(-alpha, sv.x, rv.x);      rv.y = fma(-alpha, sv.y, rv.y);
+            double2 uv;
+            uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
+            p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
+            lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+            lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !bmask[n - 1]) {
+            const int64_t i = n - 1;
+            const double pv = fma(beta, p[i], dinv[i] * r[i]);
+            const double sv = fma(beta, s[i], w[i]);
+            const double rv = fma(-alpha, sv, r[i]);
+            const double uv = dinv[i] * rv;
+            p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
+            lg = fma(rv, uv, lg);
+            lrr = fma(rv, rv, lrr);
+        }
     }
     lg = block_sum(lg, sm);
     lrr = block_sum(lrr, sm);
     if (threadIdx.x == 0) { part_g[blockIdx.x] = lg; part_rr[blockIdx.x] = lrr; }
-    // ---- the CTA that finishes last pushes the boundary entries to the peers
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&sy->ticket_v, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (threadIdx.x == 0) sy->ticket_v = 0;
-    __threadfence();
-    const unsigned long long tag = *seq + 1;
-    for (int o = 0; o < R; ++o) {
-        if (o == me) continue;
-        const int b = send_off[o], e = send_off[o + 1];
-        double* dst = reinterpret_cast<double*>(peer[o] + P2P_HDR) + dest_off[o];
-        for (int j = b + threadIdx.x; j < e; j += blockDim.x) dst[j - b] = __ldcg(&u[send_idx[j]]);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < R && threadIdx.x != me && send_off[threadIdx.x + 1] > send_off[threadIdx.x]) {
-        P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
-        __threadfence_system();
-        st_sys_u64(&m->hflag[me], tag);
-    }
 }
 
+// SpMV of the fused iteration; the CTA that finishes last runs the all-reduce through the
+// peers' mailboxes (fixed reduction order: the result does not depend on which CTA is last).
 __global__ void __launch_bounds__(PCG_THREADS, 4)
 dist_spmv_allreduce_sell_kernel(PcgDev* __restrict__ dev, int32_t n, int32_t nslices,
                                 const u32* __restrict__ slice_w, const int32_t* __restrict__ cols,
                                 const double* __restrict__ vals, const double* __restrict__ u,
                                 double* __restrict__ w, double* part_d, const double* __restrict__ part_g,
                                 const double* __restrict__ part_rr, int cnt_v, DistSync* sy,
-                                unsigned long long* seq, int R, int me, const int32_t* __restrict__ need_cnt,
+                                unsigned long long* seq, int R, int me,
                                 char* const* __restrict__ peer, double* __restrict__ out) {
     __shared__ double sm[40];
+    __shared__ double s_slot[P2P_MAXR][3];
     __shared__ int s_flag;
     if (block_done(&dev->done)) return;
     const unsigned long long s0 = *seq;
     const unsigned long long tag = s0 + 1;
     P2PMail* mine = reinterpret_cast<P2PMail*>(peer[me]);
-    // ---- wait for the neighbours' halo entries of this iteration
-    if (threadIdx.x == 0) s_flag = 0;
-    __syncthreads();
-    if (threadIdx.x < R && threadIdx.x != me && need_cnt[threadIdx.x] > 0) {
-        const long long t0 = clock64();
-        while (ld_sys_u64(&mine->hflag[threadIdx.x]) < tag) {
-            if (clock64() - t0 > P2P_SPIN_LIMIT) { s_flag = 1; break; }
-        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long now = gtime();
+        sy->dbg[12] += now - sy->dbg[8];    // V start -> S start
+        sy->dbg[9] = now;
     }
-    __syncthreads();
-    if (s_flag) {
-        if (threadIdx.x == 0) { dev->done = 1; dev->status = NODAL_CUDA_ERROR; mine->err = 1; }
-        return;
-    }
-    // ---- w = A u, partial sums of w.u
+    // (the halo part of u is complete: dist_vector_push_kernel does not finish before it is)
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -614,23 +719,7 @@ dist_spmv_allreduce_sell_kernel(PcgDev* __restrict__ dev, int32_t n, int32_t nsl
         const u32 w0 = slice_w[s];
         const int wd = (int)(slice_w[s + 1] - w0);
         const int64_t base = (int64_t)w0 * 32 + lane;
-        double acc = 0.0;
-        for (int k = 0; k < wd; k += 8) {
-            int32_t c[8];
-            double v[8], xv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < wd) {
-                    c[i] = cols[base + (int64_t)(k + i) * 32];
-                    v[i] = vals[base + (int64_t)(k + i) * 32];
-                }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < wd) xv[i] = __ldg(&u[c[i]]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < wd) acc = fma(v[i], xv[i], acc);
-        }
+        const double acc = sell_row_dot(cols, vals, base, wd, u);
         const int64_t row = s * 32 + lane;
         if (row < n) {
             w[row] = acc;
@@ -639,52 +728,52 @@ dist_spmv_allreduce_sell_kernel(PcgDev* __restrict__ dev, int32_t n, int32_t nsl
     }
     dot = block_sum(dot, sm);
     if (threadIdx.x == 0) part_d[blockIdx.x] = dot;
-    // ---- the CTA that finishes last runs the all-reduce through the peers' mailboxes
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&sy->ticket_s, 1u);
-        s_flag = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_flag) return;
-    if (threadIdx.x == 0) sy->ticket_s = 0;
-    __threadfence();
-    const double g = reduce_partials_cg(part_g, cnt_v, sm);
-    const double rr = reduce_partials_cg(part_rr, cnt_v, sm);
-    const double dl = reduce_partials_cg(part_d, (int)gridDim.x, sm);
+    if (!last_cta_arrive(sy->ticket_s, &s_flag)) return;
+    const unsigned long long ts0 = gtime();
+    double g, rr, dl;
+    reduce3_cg(part_g, cnt_v, part_rr, cnt_v, part_d, (int)gridDim.x, sm, g, rr, dl);
     const int par = (int)(s0 & 1ull);
     __syncthreads();
     if (threadIdx.x == 0) s_flag = 0;
     __syncthreads();
+    const unsigned long long ts1 = gtime();
+    unsigned long long ts2 = ts1;
     if (threadIdx.x < R) {
         P2PMail* m = reinterpret_cast<P2PMail*>(peer[threadIdx.x]);
         volatile double* slot = m->red[par][me];
         slot[0] = g; slot[1] = dl; slot[2] = rr;
-        __threadfence_system();
-        st_sys_u64(reinterpret_cast<unsigned long long*>(&m->red[par][me][3]), tag);
+        st_sys_u64(reinterpret_cast<unsigned long long*>(&m->red[par][me][3]), tag);   // release: data first
+        ts2 = gtime();
         const unsigned long long* tp = reinterpret_cast<const unsigned long long*>(&mine->red[par][threadIdx.x][3]);
         const long long t0 = clock64();
         while (ld_sys_u64(tp) != tag) {
             if (clock64() - t0 > P2P_SPIN_LIMIT) { s_flag = 1; break; }
         }
+        const volatile double* in = mine->red[par][threadIdx.x];
+        s_slot[threadIdx.x][0] = in[0]; s_slot[threadIdx.x][1] = in[1]; s_slot[threadIdx.x][2] = in[2];
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_flag) {
             dev->done = 1; dev->status = NODAL_CUDA_ERROR; mine->err = 1;
         } else {
             double sg = 0.0, sd = 0.0, sr = 0.0;
-            for (int t = 0; t < R; ++t) {
-                const volatile double* slot = mine->red[par][t];
-                sg += slot[0]; sd += slot[1]; sr += slot[2];
-            }
+            for (int t = 0; t < R; ++t) { sg += s_slot[t][0]; sd += s_slot[t][1]; sr += s_slot[t][2]; }
             out[0] = sg; out[1] = sd; out[2] = sr;
             *seq = tag;
             if (dev->iters >= dev->maxit) { dev->done = 1; dev->status = NODAL_NOT_CONVERGED; }
         }
+        const unsigned long long ts3 = gtime();
+        sy->dbg[4] += ts1 - ts0; sy->dbg[5] += ts2 - ts1; sy->dbg[6] += ts3 - ts2; sy->dbg[7] += 1;
+        sy->dbg[13] += ts0 - sy->dbg[9];    // S start -> S tail begin
+        sy->dbg[10] = ts3;
     }
+}
+
+__global__ void __launch_bounds__(DT)
+dist_mark_rows_kernel(int64_t m, const int32_t* __restrict__ rows, unsigned char* __restrict__ mask) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        mask[rows[i]] = 1;
 }
 
 static int grid_of(nodal_ctx* ctx, int64_t work) {
@@ -929,9 +1018,54 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
         }
         used_p2p = p2p;
-        DistSync* sy = static_cast<DistSync*>(dmalloc(256));
+        // boundary rows (unique, sorted) = what the communication CTA of the vector pass owns
+        int32_t* blist_dev = nullptr;
+        int32_t* push_rng_dev = nullptr;
+        unsigned char* bmask_dev = nullptr;
+        int nb_rows = 0, nbc = 1;
+        if (p2p) {
+            std::vector<int32_t> sidx((size_t)send_total);
+            if (send_total) CUDA_TRY(cudaMemcpy(sidx.data(), send_idx, sizeof(int32_t) * (size_t)send_total, cudaMemcpyDeviceToHost));
+            const std::vector<int32_t> send_h = sidx;     // per-peer blocks, each ascending
+            std::sort(sidx.begin(), sidx.end());
+            sidx.erase(std::unique(sidx.begin(), sidx.end()), sidx.end());
+            nb_rows = (int)sidx.size();
+            blist_dev = static_cast<int32_t*>(dmalloc(sizeof(int32_t) * (size_t)std::max(nb_rows, 1)));
+            bmask_dev = static_cast<unsigned char*>(dmalloc((size_t)nloc + 16));
+            if (!blist_dev || !bmask_dev) return NODAL_CUDA_ERROR;
+            CUDA_TRY(cudaMemsetAsync(bmask_dev, 0, (size_t)nloc + 16, st));
+            // CTA c of the vector pass owns blist[c*chunk, (c+1)*chunk); which send entries are those?
+            const int g2_ = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8,
+                                                   std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));
+            nbc = std::max(1, std::min(g2_, (nb_rows + PCG_THREADS - 1) / PCG_THREADS));
+            const int chunk = (nb_rows + nbc - 1) / nbc;
+            std::vector<int32_t> rng((size_t)nbc * R * 2, 0);
+            for (int cta = 0; cta < nbc; ++cta) {
+                const int k0 = cta * chunk, k1 = std::min(nb_rows, k0 + chunk);
+                for (int o = 0; o < R; ++o) {
+                    int first = send_off[o], last = send_off[o];
+                    if (k0 < k1 && o != me) {
+                        const auto b = send_h.begin() + send_off[o], e = send_h.begin() + send_off[o + 1];
+                        first = (int)(std::lower_bound(b, e, sidx[k0]) - send_h.begin());
+                        last = (int)(std::upper_bound(b, e, sidx[k1 - 1]) - send_h.begin());
+                    }
+                    rng[((size_t)cta * R + o) * 2] = first;
+                    rng[((size_t)cta * R + o) * 2 + 1] = last;
+                }
+            }
+            push_rng_dev = static_cast<int32_t*>(dmalloc(sizeof(int32_t) * rng.size()));
+            if (!push_rng_dev) return NODAL_CUDA_ERROR;
+            CUDA_TRY(cudaMemcpyAsync(push_rng_dev, rng.data(), sizeof(int32_t) * rng.size(), cudaMemcpyHostToDevice, st));
+            if (nb_rows) {
+                CUDA_TRY(cudaMemcpyAsync(blist_dev, sidx.data(), sizeof(int32_t) * (size_t)nb_rows, cudaMemcpyHostToDevice, st));
+                dist_mark_rows_kernel<<<grid_of(ctx, nb_rows), DT, 0, st>>>(nb_rows, blist_dev, bmask_dev);
+                KERNEL_CHECK();
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        DistSync* sy = static_cast<DistSync*>(dmalloc(sizeof(DistSync)));
         if (!sy) return NODAL_CUDA_ERROR;
-        CUDA_TRY(cudaMemsetAsync(sy, 0, 256, st));
+        CUDA_TRY(cudaMemsetAsync(sy, 0, sizeof(DistSync), st));
         // ---------------- local operator in the solver-private layout ----------------
         NODAL_TRY(sell_from_csr(ctx, nloc, nnz, indptr, lcols, data, &sell, st));   // resets the arena
         Mat A;
@@ -950,7 +1084,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8, want);
         }
         const bool fused = p2p && A.sell && getenv("NODAL_DIST_NO_FUSE") == nullptr;
-        const int gmax = std::max(A.g1, g2);
+        const int fuse_mode = getenv("NODAL_DIST_FUSE_MODE") ? atoi(getenv("NODAL_DIST_FUSE_MODE")) : 3;
+        const int gmax = std::max(A.g1, g2) + 1;
         const size_t vloc = align_up(sizeof(double) * (size_t)nloc, 256);
         const size_t vext = align_up(sizeof(double) * (size_t)(nloc + nhalo + 2), 256);
         NODAL_TRY(ctx_reserve(ctx, 6 * vloc + 2 * vext + 8 * align_up(sizeof(double) * gmax, 256) + 8192));
@@ -1019,14 +1154,39 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             double* cur = SC + par * 4;
             double* nxt = SC + (par ^ 1) * 4;
             if (fused) {
-                dist_vector_push_kernel<<<g2, PCG_THREADS, 0, sx>>>(
-                    dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
-                    send_idx, send_off_dev, dest_off_dev, d->peer_dev);
-                KERNEL_CHECK();
-                dist_spmv_allreduce_sell_kernel<<<A.g1, PCG_THREADS, 0, sx>>>(
-                    dev, nloc, sell->nslices, sell->slice_w, sell->cols, sell->vals, u, w, part_d, part_g,
-                    part_rr, g2, sy, d->seq, R, me, need_cnt_dev, d->peer_dev, nxt);
-                KERNEL_CHECK();
+                if (fuse_mode & 1) {
+                    dist_vector_push_kernel<<<g2, PCG_THREADS, 0, sx>>>(
+                        dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
+                        send_idx, send_off_dev, dest_off_dev, need_cnt_dev, blist_dev, nb_rows, nbc, push_rng_dev,
+                        bmask_dev, d->peer_dev);
+                    KERNEL_CHECK();
+                } else {
+                    cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
+                                                                  part_g, part_rr);
+                    KERNEL_CHECK();
+                    p2p_push_kernel<<<1, 1024, 0, sx>>>(dev, d->seq, R, me, send_idx, send_off_dev, dest_off_dev,
+                                                        d->peer_dev, u);
+                    KERNEL_CHECK();
+                }
+                if (fuse_mode & 2) {
+                    if (!(fuse_mode & 1)) {
+                        p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
+                                                               reinterpret_cast<P2PMail*>(d->shm));
+                        KERNEL_CHECK();
+                    }
+                    dist_spmv_allreduce_sell_kernel<<<A.g1, PCG_THREADS, 0, sx>>>(
+                        dev, nloc, sell->nslices, sell->slice_w, sell->cols, sell->vals, u, w, part_d, part_g,
+                        part_rr, g2, sy, d->seq, R, me, d->peer_dev, nxt);
+                    KERNEL_CHECK();
+                } else {
+                    p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
+                                                           reinterpret_cast<P2PMail*>(d->shm));
+                    KERNEL_CHECK();
+                    NODAL_TRY(launch_k1(A, dev, u, w, part_d, sx));
+                    p2p_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, d->seq, R, me, part_g, part_rr, g2, part_d, A.g1,
+                                                                d->peer_dev, nxt);
+                    KERNEL_CHECK();
+                }
                 return NODAL_OK;
             }
             cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
@@ -1116,6 +1276,19 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             }
             last_true_rr = host.rr;
             ++restarts;
+        }
+        if (getenv("NODAL_DIST_DEBUG")) {
+            unsigned long long dbg[16];
+            CUDA_TRY(cudaMemcpy(dbg, sy->dbg, sizeof(dbg), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[nodal dist rank %d] V tail: push %.2f us, flag+wait %.2f us (n=%llu); S tail: reduce %.2f us, "
+                    "publish %.2f us, wait+sum %.2f us (n=%llu)\n", me,
+                    dbg[2] ? dbg[0] / 1e3 / dbg[2] : 0.0, dbg[2] ? dbg[1] / 1e3 / dbg[2] : 0.0, dbg[2],
+                    dbg[7] ? dbg[4] / 1e3 / dbg[7] : 0.0, dbg[7] ? dbg[5] / 1e3 / dbg[7] : 0.0,
+                    dbg[7] ? dbg[6] / 1e3 / dbg[7] : 0.0, dbg[7]);
+            if (dbg[7])
+                fprintf(stderr, "[nodal dist rank %d] per iteration: V start->S start %.2f us, S start->S tail %.2f us, "
+                        "S tail end->next V start %.2f us\n", me, dbg[12] / 1e3 / dbg[7], dbg[13] / 1e3 / dbg[7],
+                        dbg[11] / 1e3 / dbg[7]);
         }
         CUDA_TRY(cudaEventRecord(ev2, st));
         CUDA_TRY(cudaEventSynchronize(ev2));

@@ -36,23 +36,7 @@ pcg_spmv_dot_sell_kernel(const PcgDev* __restrict__ dev, int32_t n, int32_t nsli
         const u32 w0 = slice_w[s];
         const int w = (int)(slice_w[s + 1] - w0);
         const int64_t base = (int64_t)w0 * 32 + lane;
-        double acc = 0.0;
-        for (int k = 0; k < w; k += 8) {
-            int32_t c[8];
-            double v[8], xv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < w) {
-                    c[i] = cols[base + (int64_t)(k + i) * 32];
-                    v[i] = vals[base + (int64_t)(k + i) * 32];
-                }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < w) xv[i] = __ldg(&p[c[i]]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < w) acc = fma(v[i], xv[i], acc);
-        }
+        const double acc = sell_row_dot(cols, vals, base, w, p);
         const int64_t r = s * 32 + lane;
         if (r < n) {
             q[r] = acc;

@@ -185,23 +185,7 @@ sell_spmv_kernel(int32_t n, int32_t nslices, const u32* __restrict__ slice_w,
         const u32 w0 = slice_w[s];
         const int w = (int)(slice_w[s + 1] - w0);
         const int64_t base = (int64_t)w0 * 32 + lane;
-        double acc = 0.0;
-        for (int k = 0; k < w; k += 8) {
-            int32_t c[8];
-            double v[8], xv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < w) {
-                    c[i] = cols[base + (int64_t)(k + i) * 32];
-                    v[i] = vals[base + (int64_t)(k + i) * 32];
-                }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < w) xv[i] = __ldg(&x[c[i]]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < w) acc = fma(v[i], xv[i], acc);
-        }
+        const double acc = sell_row_dot(cols, vals, base, w, x);
         const int64_t r = s * 32 + lane;
         if (r < n) y[r] = acc;
     }

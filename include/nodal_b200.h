@@ -134,6 +134,7 @@ int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
 #define NODAL_PCG_FORCE_CSR 1   /* do not build the sliced-ELL copy          */
 #define NODAL_PCG_NO_GRAPH 2    /* launch kernels directly (debug)           */
 #define NODAL_PCG_PROFILE 4     /* direct launches, every kernel bracketed by CUDA events */
+#define NODAL_PCG_NO_SCALE 8    /* keep D^-1 as an explicit preconditioner (no S A S pre-scaling) */
 
 /* Restarted GMRES(m) with diagonal (zero-safe) right preconditioning, FP64.
  * Replaces spsolve at nodal/nodal.py:325 when controlled / voltage sources make

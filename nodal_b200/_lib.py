@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnodal_b200.so")
 
 OK, SINGULAR, NOT_CONVERGED, BREAKDOWN, CUDA_ERROR, BAD_ARG = 0, 1, 2, 3, 4, -1
-PCG_FORCE_CSR, PCG_NO_GRAPH, PCG_PROFILE = 1, 2, 4
+PCG_FORCE_CSR, PCG_NO_GRAPH, PCG_PROFILE, PCG_NO_SCALE = 1, 2, 4, 8
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 

@@ -45,13 +45,53 @@ extern "C" int nodal_ctx_destroy(nodal_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->arena) cudaFree(ctx->arena);
+    for (auto& b : ctx->pool)
+        if (b.ptr) cudaFree(b.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
     return NODAL_OK;
 }
 
 extern "C" int64_t nodal_ctx_workspace_bytes(nodal_ctx* ctx) {
-    return ctx ? (int64_t)ctx->arena_bytes : 0;
+    if (!ctx) return 0;
+    size_t total = ctx->arena_bytes;
+    for (auto& b : ctx->pool) total += b.bytes;
+    return (int64_t)total;
+}
+
+void* ctx_pool_alloc(nodal_ctx* ctx, size_t bytes) {
+    bytes = align_up(bytes < 256 ? 256 : bytes, 256);
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); ++i) {
+        auto& b = ctx->pool[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + (1 << 20) &&
+            (best < 0 || b.bytes < ctx->pool[best].bytes))
+            best = (int)i;
+    }
+    if (best >= 0) {
+        ctx->pool[best].used = true;
+        return ctx->pool[best].ptr;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        // drop the cache and retry once
+        for (auto& b : ctx->pool)
+            if (!b.used && b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+    }
+    ctx->pool.push_back({p, bytes, true});
+    return p;
+}
+
+void ctx_pool_free(nodal_ctx* ctx, void* ptr) {
+    if (!ptr) return;
+    for (auto& b : ctx->pool)
+        if (b.ptr == ptr) { b.used = false; return; }
+    cudaFree(ptr);
 }
 
 int ctx_reserve(nodal_ctx* ctx, size_t bytes) {

@@ -52,7 +52,14 @@ struct nodal_ctx {
     uint64_t generation = 0;  // bumped by every ctx_reserve (invalidates pending results)
     // pinned host scratch for status words
     void* pinned = nullptr;
+    // cache of long-lived device buffers (solver-private matrix copies, halo tables ...):
+    // cudaMalloc / cudaFree cost milliseconds when several processes share a node
+    struct PoolBlock { void* ptr; size_t bytes; bool used; };
+    std::vector<PoolBlock> pool;
 };
+
+void* ctx_pool_alloc(nodal_ctx* ctx, size_t bytes);   // nullptr on failure
+void ctx_pool_free(nodal_ctx* ctx, void* ptr);
 
 int ctx_reserve(nodal_ctx* ctx, size_t bytes);  // make sure arena holds >= bytes (resets it)
 void* ctx_carve(nodal_ctx* ctx, size_t bytes);  // 256-B aligned bump allocation (nullptr if full)

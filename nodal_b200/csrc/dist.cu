@@ -242,6 +242,7 @@ dist_reduce_kernel(const double* __restrict__ a, const double* __restrict__ b, c
 //   w = A u ; gamma_{i+1} = r.u ; delta_{i+1} = w.u ; rr = r.r
 // SC holds two parity slots {gamma, delta, rr, alpha}; alpha == 0 in the previous slot marks the
 // first iteration after a (re)start.
+template <bool UNIT>
 __global__ void __launch_bounds__(PCG_THREADS)
 cgcg_vector_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur, const double* __restrict__ prev,
                    double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
@@ -275,33 +276,39 @@ cgcg_vector_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur
     const double2* d2 = reinterpret_cast<const double2*>(dinv);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
         double2 xv = x2[i], rv = r2[i], pv = p2[i], sv = s2[i];
-        const double2 wv = w2[i], dv = d2[i];
+        const double2 wv = w2[i];
+        double2 dv = make_double2(1.0, 1.0);
+        if (!UNIT) dv = d2[i];
         pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
         sv.x = fma(beta, sv.x, wv.x);        sv.y = fma(beta, sv.y, wv.y);
         xv.x = fma(alpha, pv.x, xv.x);       xv.y = fma(alpha, pv.y, xv.y);
         rv.x = fma(-alpha, sv.x, rv.x);      rv.y = fma(-alpha, sv.y, rv.y);
-        double2 uv;
-        uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
-        p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
-        lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+        p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv;
+        if (!UNIT) {
+            double2 uv;
+            uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
+            u2[i] = uv;
+            lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+        }
         lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = n - 1;
-        const double pv = fma(beta, p[i], dinv[i] * r[i]);
+        const double dvi = UNIT ? 1.0 : dinv[i];
+        const double pv = fma(beta, p[i], dvi * r[i]);
         const double sv = fma(beta, s[i], w[i]);
         const double rv = fma(-alpha, sv, r[i]);
-        const double uv = dinv[i] * rv;
-        p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
-        lg = fma(rv, uv, lg);
+        p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv;
+        if (!UNIT) { const double uv = dvi * rv; u[i] = uv; lg = fma(rv, uv, lg); }
         lrr = fma(rv, rv, lrr);
     }
-    lg = block_sum(lg, sm);
     lrr = block_sum(lrr, sm);
+    lg = UNIT ? lrr : block_sum(lg, sm);
     if (threadIdx.x == 0) { part_g[blockIdx.x] = lg; part_rr[blockIdx.x] = lrr; }
 }
 
 // r = b - q ; u = D^-1 r ; p = s = 0 ; partial sums of r.u, r.r, b.b
+template <bool UNIT>
 __global__ void __launch_bounds__(PCG_THREADS)
 cgcg_start_kernel(int32_t n, const double* __restrict__ b, const double* __restrict__ q,
                   const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ u,
@@ -312,8 +319,9 @@ cgcg_start_kernel(int32_t n, const double* __restrict__ b, const double* __restr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double bv = b[i];
         const double rv = bv - q[i];
-        const double uv = rv * dinv[i];
-        r[i] = rv; u[i] = uv; p[i] = 0.0; s[i] = 0.0;
+        const double uv = UNIT ? rv : rv * dinv[i];
+        r[i] = rv; p[i] = 0.0; s[i] = 0.0;
+        if (!UNIT) u[i] = uv;
         lg = fma(rv, uv, lg);
         lrr = fma(rv, rv, lrr);
         lbb = fma(bv, bv, lbb);
@@ -535,6 +543,7 @@ __device__ __forceinline__ void reduce3_cg(const double* a, int na, const double
 // waits for theirs -- so the halo exchange runs under the bulk of the kernel, and the kernel
 // cannot complete before this rank's halo is valid.  Then every CTA does its share of the
 // regular grid-stride update, skipping the boundary rows (bmask).
+template <bool UNIT>
 __global__ void __launch_bounds__(PCG_THREADS)
 dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur, const double* __restrict__ prev,
                         double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
@@ -575,22 +584,23 @@ dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict_
         const int k0 = blockIdx.x * chunk, k1 = min(nb, k0 + chunk);
         for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
             const int i = blist[k];
-            const double pv = fma(beta, p[i], dinv[i] * r[i]);
+            const double dvi = UNIT ? 1.0 : dinv[i];
+            const double pv = fma(beta, p[i], dvi * r[i]);
             const double sv = fma(beta, s[i], w[i]);
             const double rv = fma(-alpha, sv, r[i]);
-            const double uv = dinv[i] * rv;
-            p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
-            lg = fma(rv, uv, lg);
+            p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv;
+            if (!UNIT) { const double uv = dvi * rv; u[i] = uv; lg = fma(rv, uv, lg); }
             lrr = fma(rv, rv, lrr);
         }
         __syncthreads();
+        const double* src = UNIT ? r : u;    // what the peers gather: r itself when the diagonal is 1
         // entries of the (sorted) send lists that reference my rows: ranges precomputed on the host
         for (int o = 0; o < R; ++o) {
             if (o == me) continue;
             const int b = send_off[o];
             const int first = push_rng[(blockIdx.x * R + o) * 2], last = push_rng[(blockIdx.x * R + o) * 2 + 1];
             double* dst = reinterpret_cast<double*>(peer[o] + P2P_HDR) + dest_off[o];
-            for (int j = first + threadIdx.x; j < last; j += blockDim.x) dst[j - b] = u[send_idx[j]];
+            for (int j = first + threadIdx.x; j < last; j += blockDim.x) dst[j - b] = src[send_idx[j]];
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -643,22 +653,23 @@ dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict_
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
             const uchar2 mk = m2[i];
             double2 xv = x2[i], rv = r2[i], pv = p2[i], sv = s2[i];
-            const double2 wv = w2[i], dv = d2[i];
+            const double2 wv = w2[i];
+            double2 dv = make_double2(1.0, 1.0);
+            if (!UNIT) dv = d2[i];
             if (mk.x | mk.y) {   // a boundary row in this pair: element-wise, skipping the rows done above
                 if (!mk.x) {
                     pv.x = fma(beta, pv.x, dv.x * rv.x); sv.x = fma(beta, sv.x, wv.x);
                     xv.x = fma(alpha, pv.x, xv.x); rv.x = fma(-alpha, sv.x, rv.x);
-                    const double uv = dv.x * rv.x;
-                    p[2 * i] = pv.x; s[2 * i] = sv.x; x[2 * i] = xv.x; r[2 * i] = rv.x; u[2 * i] = uv;
-                    lg = fma(rv.x, uv, lg); lrr = fma(rv.x, rv.x, lrr);
+                    p[2 * i] = pv.x; s[2 * i] = sv.x; x[2 * i] = xv.x; r[2 * i] = rv.x;
+                    if (!UNIT) { const double uv = dv.x * rv.x; u[2 * i] = uv; lg = fma(rv.x, uv, lg); }
+                    lrr = fma(rv.x, rv.x, lrr);
                 }
                 if (!mk.y) {
                     pv.y = fma(beta, pv.y, dv.y * rv.y); sv.y = fma(beta, sv.y, wv.y);
                     xv.y = fma(alpha, pv.y, xv.y); rv.y = fma(-alpha, sv.y, rv.y);
-                    const double uv = dv.y * rv.y;
                     p[2 * i + 1] = pv.y; s[2 * i + 1] = sv.y; x[2 * i + 1] = xv.y; r[2 * i + 1] = rv.y;
-                    u[2 * i + 1] = uv;
-                    lg = fma(rv.y, uv, lg); lrr = fma(rv.y, rv.y, lrr);
+                    if (!UNIT) { const double uv = dv.y * rv.y; u[2 * i + 1] = uv; lg = fma(rv.y, uv, lg); }
+                    lrr = fma(rv.y, rv.y, lrr);
                 }
                 continue;
             }
@@ -666,25 +677,28 @@ dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict_
             sv.x = fma(beta, sv.x, wv.x);        sv.y = fma(beta, sv.y, wv.y);
             xv.x = fma(alpha, pv.x, xv.x);       xv.y = fma(alpha, pv.y, xv.y);
             rv.x = fma(-alpha, sv.x, rv.x);      rv.y = fma(-alpha, sv.y, rv.y);
-            double2 uv;
-            uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
-            p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
-            lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+            p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv;
+            if (!UNIT) {
+                double2 uv;
+                uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
+                u2[i] = uv;
+                lg = fma(rv.x, uv.x, lg); lg = fma(rv.y, uv.y, lg);
+            }
             lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
         }
         if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && !bmask[n - 1]) {
             const int64_t i = n - 1;
-            const double pv = fma(beta, p[i], dinv[i] * r[i]);
+            const double dvi = UNIT ? 1.0 : dinv[i];
+            const double pv = fma(beta, p[i], dvi * r[i]);
             const double sv = fma(beta, s[i], w[i]);
             const double rv = fma(-alpha, sv, r[i]);
-            const double uv = dinv[i] * rv;
-            p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv; u[i] = uv;
-            lg = fma(rv, uv, lg);
+            p[i] = pv; s[i] = sv; x[i] = fma(alpha, pv, x[i]); r[i] = rv;
+            if (!UNIT) { const double uv = dvi * rv; u[i] = uv; lg = fma(rv, uv, lg); }
             lrr = fma(rv, rv, lrr);
         }
     }
-    lg = block_sum(lg, sm);
     lrr = block_sum(lrr, sm);
+    lg = UNIT ? lrr : block_sum(lg, sm);
     if (threadIdx.x == 0) { part_g[blockIdx.x] = lg; part_rr[blockIdx.x] = lrr; }
 }
 
@@ -871,9 +885,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     nodal_sell* sell = nullptr;
     std::vector<void*> owned;   // cudaMalloc'ed buffers that outlive the arena resets
     auto dmalloc = [&](size_t bytes) -> void* {
-        void* p = nullptr;
-        if (cudaMalloc(&p, std::max<size_t>(bytes, 256)) != cudaSuccess) return nullptr;
-        owned.push_back(p);
+        void* p = ctx_pool_alloc(ctx, bytes);
+        if (p) owned.push_back(p);
         return p;
     };
     PcgDev host{};
@@ -886,6 +899,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     unsigned long long launches_per_chunk = 0;
     double host_ms_capture = 0.0;
     bool used_p2p = false;
+    double* sc = nullptr;
+    double un_rr = 0.0, un_bb = 0.0;
 
     auto run = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ev0, st));
@@ -1066,14 +1081,49 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         DistSync* sy = static_cast<DistSync*>(dmalloc(sizeof(DistSync)));
         if (!sy) return NODAL_CUDA_ERROR;
         CUDA_TRY(cudaMemsetAsync(sy, 0, sizeof(DistSync), st));
+        auto exchange = [&](double* v, cudaStream_t sx) -> int {   // fills v[nloc ..) from the owners
+            if (R == 1) return NODAL_OK;
+            if (send_total) {
+                dist_gather_kernel<<<grid_of(ctx, send_total), DT, 0, sx>>>(send_total, send_idx, v, send_buf);
+                KERNEL_CHECK();
+            }
+            NCCL_TRY(g_nccl.GroupStart());
+            for (int o = 0; o < R; ++o) {
+                if (o == me) continue;
+                if (send_cnt[o]) NCCL_TRY(g_nccl.Send(send_buf + send_off[o], send_cnt[o], ncclFloat64, o, d->comm, sx));
+                if (need_from[o]) NCCL_TRY(g_nccl.Recv(v + nloc + need_off[o], need_from[o], ncclFloat64, o, d->comm, sx));
+            }
+            NCCL_TRY(g_nccl.GroupEnd());
+            return NODAL_OK;
+        };
+        // ---------------- symmetric diagonal scaling (all ranks or none) ----------------
+        sc = static_cast<double*>(dmalloc(sizeof(double) * ((size_t)nloc + nhalo + 2) + 256));
+        if (!sc) return NODAL_CUDA_ERROR;
+        bool unit = false;
+        if (getenv("NODAL_PCG_NO_SCALE") == nullptr) {
+            int* flag = reinterpret_cast<int*>(sc + (size_t)nloc + nhalo + 2);
+            CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+            pcg_scale_factors_kernel<<<grid_of(ctx, nloc), PCG_THREADS, 0, st>>>(nloc, indptr, lcols, data, sc, flag);
+            KERNEL_CHECK();
+            if (R > 1) NCCL_TRY(g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMax, d->comm, st));
+            int* flag_h = reinterpret_cast<int*>(ctx->pinned);
+            CUDA_TRY(cudaMemcpyAsync(flag_h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            unit = (*flag_h == 0);
+            if (unit) NODAL_TRY(exchange(sc, st));     // scale factors of the halo columns
+        }
         // ---------------- local operator in the solver-private layout ----------------
-        NODAL_TRY(sell_from_csr(ctx, nloc, nnz, indptr, lcols, data, &sell, st));   // resets the arena
+        NODAL_TRY(sell_from_csr(ctx, nloc, nnz, indptr, lcols, data, &sell, st, unit ? sc : nullptr));   // resets the arena
         Mat A;
         A.n = nloc; A.nnz = nnz; A.indptr = indptr; A.indices = lcols; A.data = data;
         const double mean = (double)nnz / nloc;
         A.tpr = mean <= 2.5 ? 2 : mean <= 6.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
         const bool use_sell = (double)sell->padded <= 1.5 * (double)nnz + 1024.0;
         if (use_sell) A.sell = sell;
+        else if (unit) {
+            nodal_set_error("nodal_dist_pcg: matrix too irregular for the sliced-ELL copy");   // would need an unscaled rebuild
+            return NODAL_BAD_ARG;
+        }
         const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8,
                                               std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));
         if (A.sell) {
@@ -1084,18 +1134,22 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8, want);
         }
         const bool fused = p2p && A.sell && getenv("NODAL_DIST_NO_FUSE") == nullptr;
-        const int fuse_mode = getenv("NODAL_DIST_FUSE_MODE") ? atoi(getenv("NODAL_DIST_FUSE_MODE")) : 3;
         const int gmax = std::max(A.g1, g2) + 1;
         const size_t vloc = align_up(sizeof(double) * (size_t)nloc, 256);
         const size_t vext = align_up(sizeof(double) * (size_t)(nloc + nhalo + 2), 256);
-        NODAL_TRY(ctx_reserve(ctx, 6 * vloc + 2 * vext + 8 * align_up(sizeof(double) * gmax, 256) + 8192));
-        double* r = carve<double>(ctx, nloc);
+        NODAL_TRY(ctx_reserve(ctx, 7 * vloc + 2 * vext + 8 * align_up(sizeof(double) * gmax, 256) + 8192));
+        // the vector the SpMV gathers from lives in the layout [owned | halo] (in the peer-mapped
+        // buffer on the p2p path): u = D^-1 r in general, r itself when the diagonal is 1
+        double* ext = p2p ? reinterpret_cast<double*>(d->shm + P2P_HDR)
+                          : carve<double>(ctx, (size_t)nloc + nhalo + 2);
+        double* r = unit ? ext : carve<double>(ctx, nloc);
+        double* u = ext;
         double* q = carve<double>(ctx, nloc);                           // A x (residual checks)
         double* p = carve<double>(ctx, nloc);
         double* s = carve<double>(ctx, nloc);                           // s = A p (recurrence)
         double* w = carve<double>(ctx, nloc);                           // w = A u
-        double* u = p2p ? reinterpret_cast<double*>(d->shm + P2P_HDR)   // u = D^-1 r, [owned | halo]
-                        : carve<double>(ctx, (size_t)nloc + nhalo + 2);
+        double* bh = unit ? carve<double>(ctx, nloc) : nullptr;         // S b
+        if (unit && !bh) return NODAL_CUDA_ERROR;
         double* xe = carve<double>(ctx, (size_t)nloc + nhalo + 2);      // x in the same layout
         double* part_g = carve<double>(ctx, gmax);
         double* part_d = carve<double>(ctx, gmax);
@@ -1112,22 +1166,15 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         }
         CUDA_TRY(cudaMemsetAsync(dev, 0, sizeof(PcgDev), st));
         CUDA_TRY(cudaMemsetAsync(SC, 0, sizeof(double) * 16, st));
+        const double* b_eff = rhs_local;
+        if (unit) {
+            pcg_scale_vec_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, rhs_local, sc, bh, 0);       // b_hat = S b
+            KERNEL_CHECK();
+            pcg_scale_vec_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, x_local, sc, x_local, 1);    // x_hat = S^-1 x0
+            KERNEL_CHECK();
+            b_eff = bh;
+        }
 
-        auto exchange = [&](double* v, cudaStream_t sx) -> int {   // fills v[nloc ..) from the owners
-            if (R == 1) return NODAL_OK;
-            if (send_total) {
-                dist_gather_kernel<<<grid_of(ctx, send_total), DT, 0, sx>>>(send_total, send_idx, v, send_buf);
-                KERNEL_CHECK();
-            }
-            NCCL_TRY(g_nccl.GroupStart());
-            for (int o = 0; o < R; ++o) {
-                if (o == me) continue;
-                if (send_cnt[o]) NCCL_TRY(g_nccl.Send(send_buf + send_off[o], send_cnt[o], ncclFloat64, o, d->comm, sx));
-                if (need_from[o]) NCCL_TRY(g_nccl.Recv(v + nloc + need_off[o], need_from[o], ncclFloat64, o, d->comm, sx));
-            }
-            NCCL_TRY(g_nccl.GroupEnd());
-            return NODAL_OK;
-        };
         auto spmv_plain = [&](const double* in, double* out) -> int {
             if (A.sell) return nodal_sell_spmv(ctx, A.sell, in, out, st);
             return csr_spmv_launch(ctx, nloc, nnz, indptr, lcols, data, in, out, st);
@@ -1139,10 +1186,13 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             CUDA_TRY(cudaMemcpyAsync(xe, x_local, sizeof(double) * (size_t)nloc, cudaMemcpyDeviceToDevice, st));
             NODAL_TRY(exchange(xe, st));
             NODAL_TRY(spmv_plain(xe, q));
-            cgcg_start_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, rhs_local, q, dinv, r, u, p, s, part_g, part_rr, part_bb);
+            if (unit)
+                cgcg_start_kernel<true><<<g2, PCG_THREADS, 0, st>>>(nloc, b_eff, q, dinv, r, u, p, s, part_g, part_rr, part_bb);
+            else
+                cgcg_start_kernel<false><<<g2, PCG_THREADS, 0, st>>>(nloc, b_eff, q, dinv, r, u, p, s, part_g, part_rr, part_bb);
             KERNEL_CHECK();
-            NODAL_TRY(exchange(u, st));
-            NODAL_TRY(launch_k1(A, dev, u, w, part_d, st));
+            NODAL_TRY(exchange(ext, st));
+            NODAL_TRY(launch_k1(A, dev, ext, w, part_d, st));
             cgcg_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(dev, part_g, part_rr, part_bb, g2, part_d, A.g1, SC, 1);
             KERNEL_CHECK();
             if (R > 1) NCCL_TRY(g_nccl.AllReduce(SC, SC, 4, ncclFloat64, ncclSum, d->comm, st));
@@ -1154,55 +1204,42 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             double* cur = SC + par * 4;
             double* nxt = SC + (par ^ 1) * 4;
             if (fused) {
-                if (fuse_mode & 1) {
-                    dist_vector_push_kernel<<<g2, PCG_THREADS, 0, sx>>>(
+                // two kernels, no NCCL: push + halo wait inside the vector pass, all-reduce inside the SpMV
+                if (unit)
+                    dist_vector_push_kernel<true><<<g2, PCG_THREADS, 0, sx>>>(
                         dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
                         send_idx, send_off_dev, dest_off_dev, need_cnt_dev, blist_dev, nb_rows, nbc, push_rng_dev,
                         bmask_dev, d->peer_dev);
-                    KERNEL_CHECK();
-                } else {
-                    cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
-                                                                  part_g, part_rr);
-                    KERNEL_CHECK();
-                    p2p_push_kernel<<<1, 1024, 0, sx>>>(dev, d->seq, R, me, send_idx, send_off_dev, dest_off_dev,
-                                                        d->peer_dev, u);
-                    KERNEL_CHECK();
-                }
-                if (fuse_mode & 2) {
-                    if (!(fuse_mode & 1)) {
-                        p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
-                                                               reinterpret_cast<P2PMail*>(d->shm));
-                        KERNEL_CHECK();
-                    }
-                    dist_spmv_allreduce_sell_kernel<<<A.g1, PCG_THREADS, 0, sx>>>(
-                        dev, nloc, sell->nslices, sell->slice_w, sell->cols, sell->vals, u, w, part_d, part_g,
-                        part_rr, g2, sy, d->seq, R, me, d->peer_dev, nxt);
-                    KERNEL_CHECK();
-                } else {
-                    p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
-                                                           reinterpret_cast<P2PMail*>(d->shm));
-                    KERNEL_CHECK();
-                    NODAL_TRY(launch_k1(A, dev, u, w, part_d, sx));
-                    p2p_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, d->seq, R, me, part_g, part_rr, g2, part_d, A.g1,
-                                                                d->peer_dev, nxt);
-                    KERNEL_CHECK();
-                }
+                else
+                    dist_vector_push_kernel<false><<<g2, PCG_THREADS, 0, sx>>>(
+                        dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
+                        send_idx, send_off_dev, dest_off_dev, need_cnt_dev, blist_dev, nb_rows, nbc, push_rng_dev,
+                        bmask_dev, d->peer_dev);
+                KERNEL_CHECK();
+                dist_spmv_allreduce_sell_kernel<<<A.g1, PCG_THREADS, 0, sx>>>(
+                    dev, nloc, sell->nslices, sell->slice_w, sell->cols, sell->vals, ext, w, part_d, part_g,
+                    part_rr, g2, sy, d->seq, R, me, d->peer_dev, nxt);
+                KERNEL_CHECK();
                 return NODAL_OK;
             }
-            cgcg_vector_kernel<<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
-                                                          part_g, part_rr);
+            if (unit)
+                cgcg_vector_kernel<true><<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
+                                                                    part_g, part_rr);
+            else
+                cgcg_vector_kernel<false><<<g2, PCG_THREADS, 0, sx>>>(dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u,
+                                                                     part_g, part_rr);
             KERNEL_CHECK();
             if (p2p) {
                 p2p_push_kernel<<<1, 1024, 0, sx>>>(dev, d->seq, R, me, send_idx, send_off_dev, dest_off_dev,
-                                                    d->peer_dev, u);
+                                                    d->peer_dev, ext);
                 KERNEL_CHECK();
                 p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
                                                        reinterpret_cast<P2PMail*>(d->shm));
                 KERNEL_CHECK();
             } else {
-                NODAL_TRY(exchange(u, sx));
+                NODAL_TRY(exchange(ext, sx));
             }
-            NODAL_TRY(launch_k1(A, dev, u, w, part_d, sx));
+            NODAL_TRY(launch_k1(A, dev, ext, w, part_d, sx));
             if (p2p) {
                 p2p_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, d->seq, R, me, part_g, part_rr, g2, part_d, A.g1,
                                                             d->peer_dev, nxt);
@@ -1265,6 +1302,31 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             CUDA_TRY(cudaStreamSynchronize(st));
             host = poll[0];
             host.iters = iters_so_far;
+            if (unit) {
+                // the contract is on the UNSCALED residual: ||b - A x|| <= rtol ||b||
+                pcg_unscaled_norm_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, r, sc, rhs_local, part_rr, part_bb);
+                KERNEL_CHECK();
+                dist_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(part_rr, part_bb, nullptr, g2, SC + 12);
+                KERNEL_CHECK();
+                if (R > 1) NCCL_TRY(g_nccl.AllReduce(SC + 12, SC + 12, 2, ncclFloat64, ncclSum, d->comm, st));
+                double* un = reinterpret_cast<double*>(ctx->pinned) + 64;
+                CUDA_TRY(cudaMemcpyAsync(un, SC + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                un_rr = un[0]; un_bb = un[1];
+                const double target = rtol * rtol * un_bb;
+                if (host.rr <= host.tol2 && un_rr > target && recurrence_status == NODAL_OK &&
+                    host.iters < host.maxit && restarts < 8) {
+                    const double tol2 = host.tol2 * std::min(0.25, 0.25 * target / un_rr);
+                    const int zero = 0;
+                    CUDA_TRY(cudaMemcpyAsync(&dev->tol2, &tol2, sizeof(double), cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaMemcpyAsync(&dev->done, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    ++restarts;
+                    continue;
+                }
+                if (un_rr <= target) { host.status = NODAL_OK; break; }
+                if (host.rr <= host.tol2) { host.status = NODAL_NOT_CONVERGED; break; }
+            }
             if (host.rr <= host.tol2) { host.status = NODAL_OK; break; }
             if (recurrence_status == NODAL_NOT_CONVERGED || host.iters >= host.maxit) {
                 host.status = NODAL_NOT_CONVERGED;
@@ -1276,6 +1338,10 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             }
             last_true_rr = host.rr;
             ++restarts;
+        }
+        if (unit) {
+            pcg_scale_vec_kernel<<<g2, PCG_THREADS, 0, st>>>(nloc, x_local, sc, x_local, 0);     // x = S x_hat
+            KERNEL_CHECK();
         }
         if (getenv("NODAL_DIST_DEBUG")) {
             unsigned long long dbg[16];
@@ -1296,6 +1362,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         CUDA_TRY(cudaEventElapsedTime(&ms_solve, ev1, ev2));
         *iters_h = host.iters;
         *relres_h = host.bb > 0.0 ? sqrt(host.rr / host.bb) : 0.0;
+        if (unit && un_bb > 0.0) *relres_h = sqrt(un_rr / un_bb);
         if (stats_h) {
             stats_h[0] = host.iters;
             stats_h[1] = *relres_h;
@@ -1308,6 +1375,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             stats_h[12] = (double)halo_total;
             stats_h[13] = (double)send_total;
             stats_h[9] = used_p2p ? (fused ? 2.0 : 1.0) : 0.0;
+            stats_h[8] = unit ? 1.0 : 0.0;
         }
         return host.status;
     };
@@ -1320,7 +1388,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     if (cap) cudaStreamDestroy(cap);
     const auto h2 = std::chrono::steady_clock::now();
     if (sell) sell_free(sell);
-    for (void* p : owned) cudaFree(p);
+    for (void* p : owned) ctx_pool_free(ctx, p);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
     cudaEventDestroy(ev_poll[0]); cudaEventDestroy(ev_poll[1]);
     const auto h3 = std::chrono::steady_clock::now();

@@ -52,6 +52,8 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
     float ms_setup = 0.f, ms_solve = 0.f;
     std::vector<cudaEvent_t> prof_ev;
     double prof_ms[4] = {0, 0, 0, 0};
+    double* sc = nullptr;            // scale factors (pool)
+    double un_rr = 0.0, un_bb = 0.0;
     // everything below funnels through `finish` so the resources above are released
     auto run = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ev_t0, st));
@@ -59,12 +61,30 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
         A.n = n; A.nnz = nnz; A.indptr = indptr; A.indices = indices; A.data = data;
         const double mean = (double)nnz / n;
         A.tpr = mean <= 2.5 ? 2 : mean <= 6.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
-        if (!(flags & NODAL_PCG_FORCE_CSR)) {
-            NODAL_TRY(sell_from_csr(ctx, n, nnz, indptr, indices, data, &sell, st));
-            if ((double)sell->padded <= 1.5 * (double)nnz + 1024.0) A.sell = sell;
-        }
         const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8,
                                               std::max<int64_t>(1, ((n >> 1) + PCG_THREADS - 1) / PCG_THREADS));
+        // symmetric diagonal scaling (only with the private SELL copy, only for positive diagonals)
+        bool scaled = false;
+        if (!(flags & NODAL_PCG_FORCE_CSR)) {
+            if (!(flags & NODAL_PCG_NO_SCALE)) {
+                sc = static_cast<double*>(ctx_pool_alloc(ctx, sizeof(double) * (size_t)n + 256));
+                if (!sc) return NODAL_CUDA_ERROR;
+                int* flag = reinterpret_cast<int*>(sc + n);
+                CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+                pcg_scale_factors_kernel<<<g2, PCG_THREADS, 0, st>>>(n, indptr, indices, data, sc, flag);
+                KERNEL_CHECK();
+                int* flag_h = reinterpret_cast<int*>(ctx->pinned);
+                CUDA_TRY(cudaMemcpyAsync(flag_h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                scaled = (*flag_h == 0);
+            }
+            NODAL_TRY(sell_from_csr(ctx, n, nnz, indptr, indices, data, &sell, st, scaled ? sc : nullptr));
+            if ((double)sell->padded <= 1.5 * (double)nnz + 1024.0) A.sell = sell;
+            else scaled = false;
+            if (!scaled && sell && sc && A.sell) {   // values were scaled but the padding rule vetoed: rebuild
+                /* unreachable: scaled is only cleared here when A.sell is not used */
+            }
+        }
         if (A.sell) {
             const int64_t want = ((int64_t)sell->nslices * 32 + PCG_THREADS - 1) / PCG_THREADS;
             A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 4, want);
@@ -75,8 +95,9 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
         const size_t vec = align_up(sizeof(double) * (size_t)n, 256);
         const int gmax = std::max(A.g1, g2);
         const size_t partb = align_up(sizeof(double) * (size_t)gmax, 256);
-        NODAL_TRY(ctx_reserve(ctx, 4 * vec + 8 * partb + 4096));
+        NODAL_TRY(ctx_reserve(ctx, 5 * vec + 8 * partb + 4096));
         double* r = carve<double>(ctx, n);
+        double* bh = scaled ? carve<double>(ctx, n) : nullptr;   // S b
         double* p = carve<double>(ctx, n);
         double* q = carve<double>(ctx, n);
         double* dinv_own = nullptr;
@@ -97,6 +118,15 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             KERNEL_CHECK();
         }
         CUDA_TRY(cudaMemsetAsync(dev, 0, sizeof(PcgDev), st));
+        const double* b_eff = rhs;
+        if (scaled) {
+            if (!bh) return NODAL_CUDA_ERROR;
+            pcg_scale_vec_kernel<<<g2, PCG_THREADS, 0, st>>>(n, rhs, sc, bh, 0);     // b_hat = S b
+            KERNEL_CHECK();
+            pcg_scale_vec_kernel<<<g2, PCG_THREADS, 0, st>>>(n, x, sc, x, 1);        // x_hat = S^-1 x0
+            KERNEL_CHECK();
+            b_eff = bh;
+        }
 
         auto spmv_plain = [&](const double* in, double* out) -> int {
             if (A.sell) return nodal_sell_spmv(ctx, A.sell, in, out, st);
@@ -104,23 +134,42 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
         };
         auto start = [&](int first) -> int {  // (re)start from the current x
             NODAL_TRY(spmv_plain(x, q));
-            pcg_start_kernel<<<g2, PCG_THREADS, 0, st>>>(n, rhs, q, dinv, r, p, part_rz[1],
-                                                         part_rr[1], part_bb);
+            if (scaled)
+                pcg_start_kernel<true><<<g2, PCG_THREADS, 0, st>>>(n, b_eff, q, dinv, r, p, part_rz[1],
+                                                                   part_rr[1], part_bb);
+            else
+                pcg_start_kernel<false><<<g2, PCG_THREADS, 0, st>>>(n, b_eff, q, dinv, r, p, part_rz[1],
+                                                                    part_rr[1], part_bb);
             KERNEL_CHECK();
             pcg_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(dev, part_rr[1], part_bb, g2, rtol, maxit,
                                                           first);
             KERNEL_CHECK();
             return NODAL_OK;
         };
+        auto launch_k2 = [&](int par, cudaStream_t s) -> int {
+            if (scaled)
+                pcg_update_kernel<true><<<g2, PCG_THREADS, 0, s>>>(dev, n, part_pq[par], A.g1, part_rz[par ^ 1], g2,
+                                                                   x, p, r, q, dinv, part_rz[par], part_rr[par]);
+            else
+                pcg_update_kernel<false><<<g2, PCG_THREADS, 0, s>>>(dev, n, part_pq[par], A.g1, part_rz[par ^ 1], g2,
+                                                                    x, p, r, q, dinv, part_rz[par], part_rr[par]);
+            KERNEL_CHECK();
+            return NODAL_OK;
+        };
+        auto launch_k3 = [&](int par, cudaStream_t s) -> int {
+            if (scaled)
+                pcg_direction_kernel<true><<<g2, PCG_THREADS, 0, s>>>(dev, n, part_rz[par ^ 1], part_rz[par],
+                                                                      part_rr[par], g2, p, r, dinv);
+            else
+                pcg_direction_kernel<false><<<g2, PCG_THREADS, 0, s>>>(dev, n, part_rz[par ^ 1], part_rz[par],
+                                                                       part_rr[par], g2, p, r, dinv);
+            KERNEL_CHECK();
+            return NODAL_OK;
+        };
         auto iteration = [&](int par, cudaStream_t s) -> int {
             NODAL_TRY(launch_k1(A, dev, p, q, part_pq[par], s));
-            pcg_update_kernel<<<g2, PCG_THREADS, 0, s>>>(dev, n, part_pq[par], A.g1,
-                                                         part_rz[par ^ 1], g2, x, p, r, q, dinv,
-                                                         part_rz[par], part_rr[par]);
-            KERNEL_CHECK();
-            pcg_direction_kernel<<<g2, PCG_THREADS, 0, s>>>(dev, n, part_rz[par ^ 1], part_rz[par],
-                                                            part_rr[par], g2, p, r, dinv);
-            KERNEL_CHECK();
+            NODAL_TRY(launch_k2(par, s));
+            NODAL_TRY(launch_k3(par, s));
             return NODAL_OK;
         };
 
@@ -162,14 +211,9 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
                         CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 0], st));
                         NODAL_TRY(launch_k1(A, dev, p, q, part_pq[par], st));
                         CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 1], st));
-                        pcg_update_kernel<<<g2, PCG_THREADS, 0, st>>>(
-                            dev, n, part_pq[par], A.g1, part_rz[par ^ 1], g2, x, p, r, q, dinv,
-                            part_rz[par], part_rr[par]);
-                        KERNEL_CHECK();
+                        NODAL_TRY(launch_k2(par, st));
                         CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 2], st));
-                        pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(
-                            dev, n, part_rz[par ^ 1], part_rz[par], part_rr[par], g2, p, r, dinv);
-                        KERNEL_CHECK();
+                        NODAL_TRY(launch_k3(par, st));
                         CUDA_TRY(cudaEventRecord(prof_ev[4 * i + 3], st));
                     }
                     CUDA_TRY(cudaMemcpyAsync(&poll[0], dev, sizeof(PcgDev), cudaMemcpyDeviceToHost, st));
@@ -204,6 +248,32 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             CUDA_TRY(cudaStreamSynchronize(st));
             const int recurrence_status = host.status;
             host = poll[0];
+            if (scaled) {
+                // the contract is on the UNSCALED residual: ||b - A x|| <= rtol ||b||
+                pcg_unscaled_norm_kernel<<<g2, PCG_THREADS, 0, st>>>(n, r, sc, rhs, part_rr[0], part_bb);
+                KERNEL_CHECK();
+                std::vector<double> hp(2 * (size_t)g2);
+                CUDA_TRY(cudaMemcpyAsync(hp.data(), part_rr[0], sizeof(double) * g2, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(hp.data() + g2, part_bb, sizeof(double) * g2, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                double rr_un = 0.0, bb_un = 0.0;
+                for (int i = 0; i < g2; ++i) { rr_un += hp[i]; bb_un += hp[g2 + i]; }
+                un_rr = rr_un; un_bb = bb_un;
+                const double target = rtol * rtol * bb_un;
+                if (host.rr <= host.tol2 && rr_un > target && recurrence_status == NODAL_OK &&
+                    host.iters < host.maxit && restarts < 8) {
+                    // converged in the scaled norm only: tighten the scaled threshold and go on
+                    const double tol2 = host.tol2 * std::min(0.25, 0.25 * target / rr_un);
+                    const int zero = 0;
+                    CUDA_TRY(cudaMemcpyAsync(&dev->tol2, &tol2, sizeof(double), cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaMemcpyAsync(&dev->done, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    ++restarts;
+                    continue;
+                }
+                if (rr_un <= target) { host.status = NODAL_OK; break; }
+                if (host.rr <= host.tol2) { host.status = NODAL_NOT_CONVERGED; break; }
+            }
             if (host.rr <= host.tol2) { host.status = NODAL_OK; break; }
             if (recurrence_status == NODAL_NOT_CONVERGED || host.iters >= host.maxit) {
                 host.status = NODAL_NOT_CONVERGED;
@@ -221,8 +291,14 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
         CUDA_TRY(cudaEventSynchronize(ev_t2));
         CUDA_TRY(cudaEventElapsedTime(&ms_setup, ev_t0, ev_t1));
         CUDA_TRY(cudaEventElapsedTime(&ms_solve, ev_t1, ev_t2));
+        if (scaled) {
+            pcg_scale_vec_kernel<<<g2, PCG_THREADS, 0, st>>>(n, x, sc, x, 0);        // x = S x_hat
+            KERNEL_CHECK();
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
         *iters_h = host.iters;
         *relres_h = host.bb > 0.0 ? sqrt(host.rr / host.bb) : 0.0;
+        if (scaled && un_bb > 0.0) *relres_h = sqrt(un_rr / un_bb);
         if (stats_h) {
             stats_h[0] = host.iters;
             stats_h[1] = *relres_h;
@@ -232,6 +308,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
             stats_h[5] = A.sell ? 1.0 : 0.0;
             stats_h[6] = A.sell ? (double)sell->padded : (double)nnz;
             stats_h[7] = A.g1;
+            stats_h[12] = scaled ? 1.0 : 0.0;
             if (prof_ms[3] > 0) {
                 stats_h[8] = prof_ms[0] / prof_ms[3];
                 stats_h[9] = prof_ms[1] / prof_ms[3];
@@ -247,6 +324,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
     if (cap) cudaStreamDestroy(cap);
     for (auto& e : prof_ev) cudaEventDestroy(e);
     if (sell) { cudaStreamSynchronize(st); sell_free(sell); }
+    if (sc) ctx_pool_free(ctx, sc);
     cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1); cudaEventDestroy(ev_t2);
     cudaEventDestroy(ev_poll[0]); cudaEventDestroy(ev_poll[1]);
     return rc;

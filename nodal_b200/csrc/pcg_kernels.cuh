@@ -80,6 +80,9 @@ pcg_spmv_dot_csr_kernel(const PcgDev* __restrict__ dev, int32_t n,
 }
 
 // ---------------------------------------------------------------- K2
+// UNIT: the operator has a unit diagonal (symmetrically pre-scaled system, see pcg.cu): the
+// preconditioner is the identity, dinv is never read and r.z == r.r.
+template <bool UNIT>
 static __global__ void __launch_bounds__(PCG_THREADS)
 pcg_update_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restrict__ part_pq, int g1,
                   const double* __restrict__ part_rz_prev, int g2, double* __restrict__ x,
@@ -105,11 +108,14 @@ pcg_update_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restrict_
     const double2* d2 = reinterpret_cast<const double2*>(dinv);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
         double2 xv = x2[i], rv = r2[i];
-        const double2 pv = p2[i], qv = q2[i], dv = d2[i];
+        const double2 pv = p2[i], qv = q2[i];
         xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
         rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
         x2[i] = xv; r2[i] = rv;
-        lrz = fma(rv.x * dv.x, rv.x, lrz); lrz = fma(rv.y * dv.y, rv.y, lrz);
+        if (!UNIT) {
+            const double2 dv = d2[i];
+            lrz = fma(rv.x * dv.x, rv.x, lrz); lrz = fma(rv.y * dv.y, rv.y, lrz);
+        }
         lrr = fma(rv.x, rv.x, lrr); lrr = fma(rv.y, rv.y, lrr);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -117,15 +123,16 @@ pcg_update_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restrict_
         const double xv = fma(alpha, p[i], x[i]);
         const double rv = fma(-alpha, q[i], r[i]);
         x[i] = xv; r[i] = rv;
-        lrz = fma(rv * dinv[i], rv, lrz);
+        if (!UNIT) lrz = fma(rv * dinv[i], rv, lrz);
         lrr = fma(rv, rv, lrr);
     }
-    lrz = block_sum(lrz, sm);
     lrr = block_sum(lrr, sm);
+    lrz = UNIT ? lrr : block_sum(lrz, sm);
     if (threadIdx.x == 0) { part_rz[blockIdx.x] = lrz; part_rr[blockIdx.x] = lrr; }
 }
 
 // ---------------------------------------------------------------- K3
+template <bool UNIT>
 static __global__ void __launch_bounds__(PCG_THREADS)
 pcg_direction_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restrict__ part_rz_prev,
                      const double* __restrict__ part_rz, const double* __restrict__ part_rr, int g2,
@@ -154,19 +161,21 @@ pcg_direction_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restri
     const double2* d2 = reinterpret_cast<const double2*>(dinv);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
         double2 pv = p2[i];
-        const double2 rv = r2[i], dv = d2[i];
-        pv.x = fma(beta, pv.x, rv.x * dv.x);
-        pv.y = fma(beta, pv.y, rv.y * dv.y);
+        double2 zv = r2[i];
+        if (!UNIT) { const double2 dv = d2[i]; zv.x *= dv.x; zv.y *= dv.y; }
+        pv.x = fma(beta, pv.x, zv.x);
+        pv.y = fma(beta, pv.y, zv.y);
         p2[i] = pv;
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = n - 1;
-        p[i] = fma(beta, p[i], r[i] * dinv[i]);
+        p[i] = fma(beta, p[i], UNIT ? r[i] : r[i] * dinv[i]);
     }
 }
 
 // ---------------------------------------------------------------- start / restart
 // r = b - q (q = A x) ; p = D^-1 r ; partials of r.D^-1 r, r.r and b.b
+template <bool UNIT>
 static __global__ void __launch_bounds__(PCG_THREADS)
 pcg_start_kernel(int32_t n, const double* __restrict__ b, const double* __restrict__ q,
                  const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
@@ -178,7 +187,7 @@ pcg_start_kernel(int32_t n, const double* __restrict__ b, const double* __restri
          i += (int64_t)gridDim.x * blockDim.x) {
         const double bv = b[i];
         const double rv = bv - q[i];
-        const double zv = rv * dinv[i];
+        const double zv = UNIT ? rv : rv * dinv[i];
         r[i] = rv;
         p[i] = zv;
         lrz = fma(rv, zv, lrz);
@@ -229,6 +238,50 @@ csr_dinv_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __
     }
 }
 
+
+// ---------------------------------------------------------------- symmetric diagonal scaling
+// sc = 1 / sqrt(diag(A)).  Jacobi-PCG on A x = b is, iterate for iterate, plain CG on
+// (S A S)(S^-1 x) = S b with S = diag(sc); the scaled operator has a unit diagonal, so the
+// iteration never touches a preconditioner vector (16 n fewer bytes per iteration).
+// *flag is raised when a diagonal entry is not positive (then the unscaled kernels are used).
+static __global__ void __launch_bounds__(PCG_THREADS)
+pcg_scale_factors_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                         const double* __restrict__ data, double* __restrict__ sc, int* __restrict__ flag) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        double dg = 0.0;
+        for (int32_t j = indptr[r]; j < indptr[r + 1]; ++j)
+            if (indices[j] == r) dg += data[j];
+        if (dg > 0.0) sc[r] = 1.0 / sqrt(dg);
+        else { sc[r] = 1.0; *flag = 1; }
+    }
+}
+
+// out = in * sc (mode 0) or in / sc (mode 1); in and out may alias
+static __global__ void __launch_bounds__(PCG_THREADS)
+pcg_scale_vec_kernel(int32_t n, const double* in, const double* __restrict__ sc, double* out, int mode) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = mode ? in[i] / sc[i] : in[i] * sc[i];
+}
+
+// partial sums of the UNSCALED residual norm (r_hat / sc)^2 and of b^2
+static __global__ void __launch_bounds__(PCG_THREADS)
+pcg_unscaled_norm_kernel(int32_t n, const double* __restrict__ rhat, const double* __restrict__ sc,
+                         const double* __restrict__ b, double* __restrict__ part_rr,
+                         double* __restrict__ part_bb) {
+    __shared__ double sm[40];
+    double lrr = 0.0, lbb = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double rv = rhat[i] / sc[i];
+        lrr = fma(rv, rv, lrr);
+        lbb = fma(b[i], b[i], lbb);
+    }
+    lrr = block_sum(lrr, sm);
+    lbb = block_sum(lbb, sm);
+    if (threadIdx.x == 0) { part_rr[blockIdx.x] = lrr; part_bb[blockIdx.x] = lbb; }
+}
 
 // ---------------------------------------------------------------- operator handle
 struct Mat {

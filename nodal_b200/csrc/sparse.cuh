@@ -8,6 +8,7 @@
 // in their original order and columns in CSR order, so the per-row summation order is
 // the CSR one.  Padding entries have val 0 and col = the row itself.
 struct nodal_sell {
+    nodal_ctx* ctx = nullptr;   // owner of the buffers (pool)
     int device = 0;
     int32_t n = 0;
     int32_t nslices = 0;
@@ -20,7 +21,8 @@ struct nodal_sell {
 };
 
 int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
-                  const int32_t* indices, const double* data, nodal_sell** out, cudaStream_t st);
+                  const int32_t* indices, const double* data, nodal_sell** out, cudaStream_t st,
+                  const double* sc = nullptr);   // sc: optional row/column scale factors (S A S)
 void sell_free(nodal_sell* m);
 
 // y = A x on the generic CSR path

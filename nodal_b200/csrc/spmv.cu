@@ -87,8 +87,8 @@ sell_widths_kernel(int32_t n, int32_t nslices, const int32_t* __restrict__ indpt
 __global__ void __launch_bounds__(SPMV_THREADS)
 sell_fill_kernel(int32_t n, int32_t nslices, const int32_t* __restrict__ indptr,
                  const int32_t* __restrict__ indices, const double* __restrict__ data,
-                 const u32* __restrict__ slice_w, int32_t* __restrict__ cols,
-                 double* __restrict__ vals, double* __restrict__ dinv) {
+                 const u32* __restrict__ slice_w, const double* __restrict__ sc,
+                 int32_t* __restrict__ cols, double* __restrict__ vals, double* __restrict__ dinv) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -105,6 +105,7 @@ sell_fill_kernel(int32_t n, int32_t nslices, const int32_t* __restrict__ indptr,
             if (b + (int32_t)k < e) {
                 c = indices[b + k];
                 v = data[b + k];
+                if (sc) v = (v * sc[r]) * sc[c];      // symmetric scaling: S A S
                 if (c == r) diag += v;
             }
             cols[base + (int64_t)k * 32] = c;
@@ -117,17 +118,19 @@ sell_fill_kernel(int32_t n, int32_t nslices, const int32_t* __restrict__ indptr,
 void sell_free(nodal_sell* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    if (m->slice_w) cudaFree(m->slice_w);
-    if (m->cols) cudaFree(m->cols);
-    if (m->vals) cudaFree(m->vals);
-    if (m->dinv) cudaFree(m->dinv);
+    ctx_pool_free(m->ctx, m->slice_w);
+    ctx_pool_free(m->ctx, m->cols);
+    ctx_pool_free(m->ctx, m->vals);
+    ctx_pool_free(m->ctx, m->dinv);
     delete m;
 }
 
 int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
-                  const int32_t* indices, const double* data, nodal_sell** out, cudaStream_t st) {
+                  const int32_t* indices, const double* data, nodal_sell** out, cudaStream_t st,
+                  const double* sc) {
     *out = nullptr;
     nodal_sell* m = new nodal_sell();
+    m->ctx = ctx;
     m->device = ctx->device;
     m->n = n;
     m->nnz = nnz;
@@ -144,8 +147,17 @@ int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
             return fail(NODAL_CUDA_ERROR);                                                   \
         }                                                                                    \
     } while (0)
-    CT(cudaMalloc(&m->slice_w, sizeof(u32) * (size_t)(ns + 1)));
-    CT(cudaMalloc(&m->dinv, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+#define PA(field, type, bytes)                                                               \
+    do {                                                                                     \
+        m->field = static_cast<type*>(ctx_pool_alloc(ctx, (bytes)));                         \
+        if (!m->field) {                                                                     \
+            nodal_set_error("%s:%d: out of device memory (%zu bytes)", __FILE__, __LINE__,   \
+                            (size_t)(bytes));                                                \
+            return fail(NODAL_CUDA_ERROR);                                                   \
+        }                                                                                    \
+    } while (0)
+    PA(slice_w, u32, sizeof(u32) * (size_t)(ns + 1));
+    PA(dinv, double, sizeof(double) * (size_t)(n > 0 ? n : 1));
     CT(cudaMemsetAsync(m->slice_w, 0, sizeof(u32) * (size_t)(ns + 1), st));
     if (n == 0) { *out = m; return NODAL_OK; }
     const int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -163,10 +175,11 @@ int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
     CT(cudaStreamSynchronize(st));
     m->padded = (int64_t)host_tot[0] * 32;
     const size_t alloc = (size_t)(m->padded > 0 ? m->padded : 32);
-    CT(cudaMalloc(&m->cols, sizeof(int32_t) * alloc));
-    CT(cudaMalloc(&m->vals, sizeof(double) * alloc));
+    PA(cols, int32_t, sizeof(int32_t) * alloc);
+    PA(vals, double, sizeof(double) * alloc);
+#undef PA
     sell_fill_kernel<<<grid, SPMV_THREADS, 0, st>>>(n, m->nslices, indptr, indices, data,
-                                                    m->slice_w, m->cols, m->vals, m->dinv);
+                                                    m->slice_w, sc, m->cols, m->vals, m->dinv);
     CT(cudaGetLastError());
 #undef CT
     *out = m;
@@ -196,7 +209,7 @@ extern "C" int nodal_sell_create(nodal_ctx* ctx, int32_t n, int64_t nnz, const i
                                  void* stream) {
     if (!ctx || n < 0 || !out) return NODAL_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    return sell_from_csr(ctx, n, nnz, indptr, indices, data, out, (cudaStream_t)stream);
+    return sell_from_csr(ctx, n, nnz, indptr, indices, data, out, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int nodal_sell_destroy(nodal_sell* m) {

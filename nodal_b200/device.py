@@ -205,7 +205,7 @@ class Device:
         info = dict(solver="pcg", status=st, iterations=iters.value, relres=relres.value,
                     restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4],
                     format="sell32" if stats[5] else "csr", stored_nnz=int(stats[6]),
-                    spmv_grid=int(stats[7]))
+                    spmv_grid=int(stats[7]), scaled=bool(stats[12]))
         if stats[11]:
             info["kernel_ms"] = dict(spmv_dot=stats[8], update=stats[9], direction=stats[10],
                                      samples=int(stats[11]))

@@ -104,7 +104,7 @@ class DistPCG:
                     restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4],
                     format="sell32" if stats[5] else "csr", stored_nnz=int(stats[6]),
                     halo_recv=int(stats[12]), halo_send=int(stats[13]), nnz=int(data.numel()),
-                    comm={0: "nccl", 1: "p2p", 2: "p2p-fused"}[int(stats[9])],
+                    comm={0: "nccl", 1: "p2p", 2: "p2p-fused"}[int(stats[9])], scaled=bool(stats[8]),
                     host_ms=dict(run=stats[14], graph_teardown=stats[15], buffer_teardown=stats[11],
                                  graph_capture=stats[10]))
         return x, info

@@ -64,16 +64,46 @@ compact_kernel(const u64* __restrict__ ukey, const double* __restrict__ uval,
     }
 }
 
+// indptr[q] = position of the first kept entry with row >= q.  Short runs of empty rows are
+// filled by the thread that sees the row change; long runs (a rank of the multi-GPU path owns
+// 1/R of the rows of a global-shaped matrix) go to a gap list that a second kernel fills in
+// parallel.
+struct RowGap { int32_t first, last, value; int32_t pad; };
+constexpr int ROWPTR_INLINE = 32;
+constexpr int ROWPTR_MAX_GAPS = 4096;
+
+__device__ __forceinline__ void fill_rows(int32_t first, int32_t last, int32_t value,
+                                          int32_t* __restrict__ indptr, RowGap* gaps, unsigned int* ngaps) {
+    if (last - first < ROWPTR_INLINE) {
+        for (int32_t q = first; q <= last; ++q) indptr[q] = value;
+        return;
+    }
+    const unsigned int slot = atomicAdd(ngaps, 1u);
+    if (slot < ROWPTR_MAX_GAPS) { gaps[slot].first = first; gaps[slot].last = last; gaps[slot].value = value; }
+    else for (int32_t q = first; q <= last; ++q) indptr[q] = value;   // list full: do it here
+}
+
 __global__ void __launch_bounds__(CB_THREADS)
 row_ptr_kernel(const int32_t* __restrict__ krow, int64_t nnz, int32_t n,
-               int32_t* __restrict__ indptr) {
+               int32_t* __restrict__ indptr, RowGap* gaps, unsigned int* ngaps) {
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
          p += (int64_t)gridDim.x * blockDim.x) {
         const int32_t r = krow[p];
         const int32_t rp = p ? krow[p - 1] : -1;
-        for (int32_t q = rp + 1; q <= r; ++q) indptr[q] = (int32_t)p;
-        if (p == nnz - 1)
-            for (int32_t q = r + 1; q <= n; ++q) indptr[q] = (int32_t)nnz;
+        if (r != rp) fill_rows(rp + 1, r, (int32_t)p, indptr, gaps, ngaps);
+        if (p == nnz - 1) fill_rows(r + 1, n, (int32_t)nnz, indptr, gaps, ngaps);
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+row_ptr_gaps_kernel(int32_t* __restrict__ indptr, const RowGap* __restrict__ gaps,
+                    const unsigned int* __restrict__ ngaps) {
+    const unsigned int count = min(*ngaps, (unsigned int)ROWPTR_MAX_GAPS);
+    for (unsigned int g = 0; g < count; ++g) {
+        const RowGap gp = gaps[g];
+        for (int64_t q = (int64_t)gp.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= gp.last;
+             q += (int64_t)gridDim.x * blockDim.x)
+            indptr[q] = gp.value;
     }
 }
 
@@ -196,8 +226,15 @@ extern "C" int nodal_csr_fetch(nodal_ctx* ctx, int32_t n, int64_t nnz, int32_t* 
     compact_kernel<<<grid_for(ctx, p.useg, CB_THREADS), CB_THREADS, 0, st>>>(
         p.ukey, p.uval, p.keep_scan, p.keep, p.useg, p.colbits, indices, data, p.krow);
     KERNEL_CHECK();
-    row_ptr_kernel<<<grid_for(ctx, nnz, CB_THREADS), CB_THREADS, 0, st>>>(p.krow, nnz, n, indptr);
+    RowGap* gaps = reinterpret_cast<RowGap*>(ctx_pool_alloc(ctx, sizeof(RowGap) * ROWPTR_MAX_GAPS + 256));
+    if (!gaps) return NODAL_CUDA_ERROR;
+    unsigned int* ngaps = reinterpret_cast<unsigned int*>(gaps + ROWPTR_MAX_GAPS);
+    CUDA_TRY(cudaMemsetAsync(ngaps, 0, sizeof(unsigned int), st));
+    row_ptr_kernel<<<grid_for(ctx, nnz, CB_THREADS), CB_THREADS, 0, st>>>(p.krow, nnz, n, indptr, gaps, ngaps);
     KERNEL_CHECK();
+    row_ptr_gaps_kernel<<<ctx->num_sms * 4, CB_THREADS, 0, st>>>(indptr, gaps, ngaps);
+    KERNEL_CHECK();
+    ctx_pool_free(ctx, gaps);   // stream-ordered reuse only
     g_pending = PendingCsr();
     return NODAL_OK;
 }

@@ -165,3 +165,19 @@ def test_empty_and_tiny(device, tmp_path):
     assert cs.G.indptr.cpu().numpy().tolist() == [0, 1]
     assert cs.G.data.cpu().numpy().tolist() == [0.5]
     assert cs.A_host.tolist() == [3.0]
+
+
+def test_row_pointer_with_long_empty_runs(device):
+    """Entries confined to a few row ranges of a much larger matrix (what a rank of the
+    multi-GPU path builds): long runs of empty rows go through the parallel gap fill."""
+    rng = np.random.default_rng(11)
+    n = 3_000_000
+    cb = colbits_for(n)
+    rows = np.concatenate([rng.integers(400_000, 400_500, 5000), rng.integers(1_000_000, 1_300_000, 200_000),
+                           np.array([2_999_999, 17])])
+    cols = rng.integers(0, n, len(rows))
+    vals = rng.standard_normal(len(rows))
+    keys = (rows.astype(np.int64) << cb) | cols.astype(np.int64)
+    ip, ix, dt, rhs = csr_build_raw(device, keys, vals, n, cb)
+    wip, wix, wdt, wrhs = reduce_triples(rows.astype(np.int32), cols.astype(np.int32), vals, n)
+    assert np.array_equal(ip, wip) and np.array_equal(ix, wix) and np.array_equal(dt, wdt)

@@ -96,7 +96,9 @@ class TableNetlist(Netlist):
 
     @property
     def degrees(self):
-        raise AttributeError("TableNetlist does not keep per-node degrees")
+        if getattr(self, "_degrees", None) is not None:
+            return self._degrees
+        raise AttributeError("this TableNetlist does not keep per-node degrees")
 
     def is_resistive(self):
         return self._table.is_resistive()

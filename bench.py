@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=4096, help="grid side (4096 -> 16.7M nodes, config C5a)")
-    ap.add_argument("--ref-grid", type=int, default=200, help="grid side of the bounded CPU sample")
+    ap.add_argument("--ref-grid", type=int, default=400, help="grid side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1128,7 +1128,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
                                               std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));
         if (A.sell) {
             const int64_t want = ((int64_t)sell->nslices * 32 + PCG_THREADS - 1) / PCG_THREADS;
-            A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 4, want);
+            const int per_sm = getenv("NODAL_SPMV_CTAS_PER_SM") ? atoi(getenv("NODAL_SPMV_CTAS_PER_SM")) : 4;
+            A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * per_sm, want);
         } else {
             const int64_t want = ((int64_t)nloc * A.tpr + PCG_THREADS - 1) / PCG_THREADS;
             A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8, want);
@@ -1259,6 +1260,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             const auto c0 = std::chrono::steady_clock::now();
             const unsigned long long before = g_nodal_launches;
             CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+            if (A.sell) NODAL_TRY(sell_set_l2_window(ctx, A.sell, cap));
             CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
             int crc = NODAL_OK;
             for (int i = 0; i < CH && crc == NODAL_OK; ++i) crc = iteration(i & 1, cap);
@@ -1385,7 +1387,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
     const auto h1 = std::chrono::steady_clock::now();
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
-    if (cap) cudaStreamDestroy(cap);
+    if (cap) { sell_clear_l2_window(cap); cudaStreamDestroy(cap); }
     const auto h2 = std::chrono::steady_clock::now();
     if (sell) sell_free(sell);
     for (void* p : owned) ctx_pool_free(ctx, p);

@@ -182,6 +182,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
         if (use_graph) {
             const unsigned long long before = g_nodal_launches;
             CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+            if (A.sell) NODAL_TRY(sell_set_l2_window(ctx, A.sell, cap));
             CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
             int crc = NODAL_OK;
             for (int i = 0; i < PCG_CHUNK && crc == NODAL_OK; ++i) crc = iteration(i & 1, cap);
@@ -321,7 +322,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
     rc = run();
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
-    if (cap) cudaStreamDestroy(cap);
+    if (cap) { sell_clear_l2_window(cap); cudaStreamDestroy(cap); }
     for (auto& e : prof_ev) cudaEventDestroy(e);
     if (sell) { cudaStreamSynchronize(st); sell_free(sell); }
     if (sc) ctx_pool_free(ctx, sc);

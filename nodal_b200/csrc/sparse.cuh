@@ -15,8 +15,9 @@ struct nodal_sell {
     int64_t padded = 0;        // stored entries (incl. padding)
     int64_t nnz = 0;
     u32* slice_w = nullptr;    // [nslices + 1]: exclusive scan of slice widths (units: k-steps)
-    int32_t* cols = nullptr;   // [padded]
+    int32_t* cols = nullptr;   // [padded]  (second half of the vals block)
     double* vals = nullptr;    // [padded]
+    size_t store_bytes = 0;    // bytes of the [vals | cols] block
     double* dinv = nullptr;    // [n] 1 / diagonal (1 where the diagonal is 0)
 };
 
@@ -24,6 +25,8 @@ int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
                   const int32_t* indices, const double* data, nodal_sell** out, cudaStream_t st,
                   const double* sc = nullptr);   // sc: optional row/column scale factors (S A S)
 void sell_free(nodal_sell* m);
+int sell_set_l2_window(nodal_ctx* ctx, const nodal_sell* m, cudaStream_t st);   // see spmv.cu
+void sell_clear_l2_window(cudaStream_t st);
 
 // y = A x on the generic CSR path
 int csr_spmv_launch(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,

@@ -1,4 +1,6 @@
 // SpMV kernels: generic CSR (sub-warp per row) and the solver-private sliced-ELL format.
+#include <algorithm>
+
 #include "sparse.cuh"
 
 constexpr int SPMV_THREADS = 256;
@@ -119,8 +121,7 @@ void sell_free(nodal_sell* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     ctx_pool_free(m->ctx, m->slice_w);
-    ctx_pool_free(m->ctx, m->cols);
-    ctx_pool_free(m->ctx, m->vals);
+    ctx_pool_free(m->ctx, m->vals);      // vals and cols share one block
     ctx_pool_free(m->ctx, m->dinv);
     delete m;
 }
@@ -175,8 +176,10 @@ int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
     CT(cudaStreamSynchronize(st));
     m->padded = (int64_t)host_tot[0] * 32;
     const size_t alloc = (size_t)(m->padded > 0 ? m->padded : 32);
-    PA(cols, int32_t, sizeof(int32_t) * alloc);
-    PA(vals, double, sizeof(double) * alloc);
+    // one block [vals | cols] so that a single L2 access-policy window can cover the operator
+    PA(vals, double, sizeof(double) * alloc + sizeof(int32_t) * alloc);
+    m->cols = reinterpret_cast<int32_t*>(m->vals + alloc);
+    m->store_bytes = (sizeof(double) + sizeof(int32_t)) * alloc;
 #undef PA
     sell_fill_kernel<<<grid, SPMV_THREADS, 0, st>>>(n, m->nslices, indptr, indices, data,
                                                     m->slice_w, sc, m->cols, m->vals, m->dinv);
@@ -230,4 +233,42 @@ extern "C" int nodal_sell_spmv(nodal_ctx* ctx, const nodal_sell* m, const double
         m->n, m->nslices, m->slice_w, m->cols, m->vals, x, y);
     KERNEL_CHECK();
     return NODAL_OK;
+}
+
+// ---------------------------------------------------------------- L2 residency
+// Every CG iteration streams the whole operator once.  When the operator is not much larger
+// than the 126 MB L2 (a rank of the multi-GPU path holds 1/R of it) plain LRU gets ~0 hits
+// out of a cyclic sweep; pinning a fraction of it as "persisting" keeps that fraction
+// resident from one iteration to the next.  Applied to the stream the iteration graph is
+// captured on, so every kernel node inherits the window.
+// MEASURED (r1, B200): a loss.  With the window the vector-update kernels that share the
+// graph slow down by 1.5-1.8x (2 x 2.1 M rows/rank: 25.8 -> 47.7 us; 1 GPU, 16.7 M rows:
+// 432 -> 674 us per iteration) while the SpMV gains 3 %; the set-aside takes L2 away from
+// the write-back traffic of the streaming kernels.  Kept opt-in (NODAL_L2_WINDOW=1) only.
+int sell_set_l2_window(nodal_ctx* ctx, const nodal_sell* m, cudaStream_t st) {
+    if (!m || !m->vals || !getenv("NODAL_L2_WINDOW")) return NODAL_OK;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return NODAL_OK;
+    const size_t persist = (size_t)prop.persistingL2CacheMaxSize;
+    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    const size_t window = std::min<size_t>(m->store_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.base_ptr = m->vals;
+    attr.accessPolicyWindow.num_bytes = window;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.85 * (double)persist / (double)window);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return NODAL_OK;
+}
+
+void sell_clear_l2_window(cudaStream_t st) {
+    if (!getenv("NODAL_L2_WINDOW")) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaCtxResetPersistingL2Cache();
 }

@@ -230,7 +230,28 @@ def run_ours(args):
                "ms_per_step": e2e_ms, "R": r_e2e,
                "api": "nodal_b200.Circuit(netlist, sparse=True).solve() on a host TableNetlist (pinned columns)"}
 
+    if world > 1:
+        runner.step_e2e()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            r_e2e, _ = runner.step_e2e()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        hb = torch.tensor([float(runner.local.nbytes), float(runner._host_x.numel() * 8)], device="cuda",
+                          dtype=torch.float64)
+        dist.all_reduce(hb)
+        e2e_ms = float(t.item()) / args.steps
+        e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
+               "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()),
+               "ms_per_step": e2e_ms, "R": r_e2e,
+               "api": "nodal_b200.dist.GridRunner.step_e2e(): per-rank pinned component table up, "
+                      "per-rank slice of the solution down (bytes summed over ranks)"}
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (PCG SpMV + dot), per-launch time from CUDA events
     peak, peak_src = load_peaks()

@@ -1050,7 +1050,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             if (!blist_dev || !bmask_dev) return NODAL_CUDA_ERROR;
             CUDA_TRY(cudaMemsetAsync(bmask_dev, 0, (size_t)nloc + 16, st));
             // CTA c of the vector pass owns blist[c*chunk, (c+1)*chunk); which send entries are those?
-            const int g2_ = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8,
+            const int g2_per_sm_ = getenv("NODAL_DIST_G2") ? atoi(getenv("NODAL_DIST_G2")) : 8;
+            const int g2_ = (int)std::min<int64_t>((int64_t)ctx->num_sms * g2_per_sm_,
                                                    std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));
             nbc = std::max(1, std::min(g2_, (nb_rows + PCG_THREADS - 1) / PCG_THREADS));
             const int chunk = (nb_rows + nbc - 1) / nbc;
@@ -1124,7 +1125,8 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
             nodal_set_error("nodal_dist_pcg: matrix too irregular for the sliced-ELL copy");   // would need an unscaled rebuild
             return NODAL_BAD_ARG;
         }
-        const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8,
+        const int g2_per_sm = getenv("NODAL_DIST_G2") ? atoi(getenv("NODAL_DIST_G2")) : 8;
+        const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * g2_per_sm,
                                               std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));
         if (A.sell) {
             const int64_t want = ((int64_t)sell->nslices * 32 + PCG_THREADS - 1) / PCG_THREADS;

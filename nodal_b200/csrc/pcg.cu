@@ -61,7 +61,8 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
         A.n = n; A.nnz = nnz; A.indptr = indptr; A.indices = indices; A.data = data;
         const double mean = (double)nnz / n;
         A.tpr = mean <= 2.5 ? 2 : mean <= 6.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
-        const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * 8,
+        const int g2_per_sm = getenv("NODAL_PCG_G2") ? atoi(getenv("NODAL_PCG_G2")) : 5;   // CTAs per SM of the vector kernels (measured best)
+        const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * g2_per_sm,
                                               std::max<int64_t>(1, ((n >> 1) + PCG_THREADS - 1) / PCG_THREADS));
         // symmetric diagonal scaling (only with the private SELL copy, only for positive diagonals)
         bool scaled = false;

@@ -91,8 +91,13 @@ pcg_update_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restrict_
                   double* __restrict__ part_rz, double* __restrict__ part_rr) {
     __shared__ double sm[40];
     if (block_done(&dev->done)) return;
-    const double pq = reduce_partials(part_pq, g1, sm);
-    const double rz = reduce_partials(part_rz_prev, g2, sm);
+    double pq, rz, unused;
+    if (g1 <= 8 * PCG_THREADS && g2 <= 8 * PCG_THREADS) {
+        reduce_partials3(part_pq, g1, part_rz_prev, g2, nullptr, 0, sm, pq, rz, unused);
+    } else {
+        pq = reduce_partials(part_pq, g1, sm);
+        rz = reduce_partials(part_rz_prev, g2, sm);
+    }
     if (!(pq > 0.0)) {  // not SPD (or NaN): stop, x keeps the last good iterate
         if (blockIdx.x == 0 && threadIdx.x == 0) { dev->done = 1; dev->status = NODAL_BREAKDOWN; }
         return;
@@ -140,9 +145,14 @@ pcg_direction_kernel(PcgDev* __restrict__ dev, int32_t n, const double* __restri
                      const double* __restrict__ dinv) {
     __shared__ double sm[40];
     if (block_done(&dev->done)) return;
-    const double rz_old = reduce_partials(part_rz_prev, g2, sm);
-    const double rz_new = reduce_partials(part_rz, g2, sm);
-    const double rr = reduce_partials(part_rr, g2, sm);
+    double rz_old, rz_new, rr;
+    if (g2 <= 8 * PCG_THREADS) {
+        reduce_partials3(part_rz_prev, g2, part_rz, g2, part_rr, g2, sm, rz_old, rz_new, rr);
+    } else {
+        rz_old = reduce_partials(part_rz_prev, g2, sm);
+        rz_new = reduce_partials(part_rz, g2, sm);
+        rr = reduce_partials(part_rr, g2, sm);
+    }
     const bool conv = rr <= dev->tol2;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const int it = dev->iters + 1;

@@ -123,19 +123,34 @@ class GridRunner:
         self.owner = int(np.searchsorted(self.bounds, self.probe_row, side="right") - 1)
         self.pcg = DistPCG(dev, rank, world)
         self.dtab = dev.upload_table(self.local)
+        self._host_x = None
 
-    def step(self, _unused=None):
+    def step_e2e(self):
+        """Same step with HOST buffers: the rank's component table goes up from pinned host
+        memory and its slice of the solution comes back to pinned host memory."""
+        torch = self.dev.torch
+        if getattr(self.local, "_pinned", None) is None:
+            self.local.pin_memory()
+            nloc = int(self.bounds[self.rank + 1] - self.bounds[self.rank])
+            self._host_x = torch.empty(nloc, dtype=torch.float64).pin_memory()
+        return self.step(upload=True)
+
+    def step(self, _unused=None, upload=False):
         import time
         import torch.distributed as dist
         torch = self.dev.torch
         t0 = time.perf_counter()
-        indptr, indices, data, rhs = self.pcg.assemble_local(self.local, self.bounds, dtab=self.dtab)
+        dtab = self.dev.upload_table(self.local) if upload else self.dtab
+        indptr, indices, data, rhs = self.pcg.assemble_local(self.local, self.bounds, dtab=dtab)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         x, info = self.pcg.solve(self.n, self.bounds, indptr, indices, data, rhs, rtol=self.rtol)
         t2 = time.perf_counter()
         info["assemble_wall_ms"] = (t1 - t0) * 1e3
         info["solve_wall_ms"] = (t2 - t1) * 1e3
+        if upload:
+            self._host_x.copy_(x, non_blocking=True)
+            torch.cuda.synchronize()
         r = torch.zeros(1, dtype=torch.float64, device=self.dev.dev)
         if self.rank == self.owner:
             r[0] = x[self.probe_row - int(self.bounds[self.rank])]

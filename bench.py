@@ -29,6 +29,8 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 import numpy as np  # noqa: E402
 
 RTOL = 1e-10
+# DRAM traffic of one pcg_spmv_dot_sell_kernel launch from the committed ncu capture (grid side -> bytes)
+NCU_DRAM_BYTES_PER_LAUNCH = {4096: 1.143079e9 + 0.128681e9}
 KNIGHT_LIMIT = 4 / np.pi - 0.5       # infinite-grid knight's-move resistance
 
 
@@ -264,7 +266,10 @@ def run_ours(args):
             bytes_spmv = 12.0 * nnz + 20.0 * n_unknowns
             achieved = bytes_spmv / (km["spmv_dot"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "pcg_spmv_dot_sell_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(N),
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
+                                      "profiles/r1_pcg_kernels_ncu_full_raw.csv" if N in NCU_DRAM_BYTES_PER_LAUNCH else None,
                     "algorithmic_bytes_per_launch": bytes_spmv, "ms_per_launch": km["spmv_dot"],
                     "samples": km["samples"],
                     "other_kernels_ms": {"update": km["update"], "direction": km["direction"]},

@@ -704,7 +704,7 @@ dist_vector_push_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict_
 
 // SpMV of the fused iteration; the CTA that finishes last runs the all-reduce through the
 // peers' mailboxes (fixed reduction order: the result does not depend on which CTA is last).
-__global__ void __launch_bounds__(PCG_THREADS, 4)
+__global__ void __launch_bounds__(PCG_THREADS, 5)
 dist_spmv_allreduce_sell_kernel(PcgDev* __restrict__ dev, int32_t n, int32_t nslices,
                                 const u32* __restrict__ slice_w, const int32_t* __restrict__ cols,
                                 const double* __restrict__ vals, const double* __restrict__ u,
@@ -1130,7 +1130,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
                                               std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));
         if (A.sell) {
             const int64_t want = ((int64_t)sell->nslices * 32 + PCG_THREADS - 1) / PCG_THREADS;
-            const int per_sm = getenv("NODAL_SPMV_CTAS_PER_SM") ? atoi(getenv("NODAL_SPMV_CTAS_PER_SM")) : 4;
+            const int per_sm = getenv("NODAL_SPMV_CTAS_PER_SM") ? atoi(getenv("NODAL_SPMV_CTAS_PER_SM")) : 5;
             A.g1 = (int)std::min<int64_t>((int64_t)ctx->num_sms * per_sm, want);
         } else {
             const int64_t want = ((int64_t)nloc * A.tpr + PCG_THREADS - 1) / PCG_THREADS;

@@ -21,7 +21,8 @@ __device__ __forceinline__ bool block_done(const int* done) {
 }
 
 // ---------------------------------------------------------------- K1
-static __global__ void __launch_bounds__(PCG_THREADS, 4)
+template <int MINB>
+static __global__ void __launch_bounds__(PCG_THREADS, MINB)
 pcg_spmv_dot_sell_kernel(const PcgDev* __restrict__ dev, int32_t n, int32_t nslices,
                          const u32* __restrict__ slice_w, const int32_t* __restrict__ cols,
                          const double* __restrict__ vals, const double* __restrict__ p,
@@ -304,14 +305,22 @@ struct Mat {
     const double* data = nullptr;
     int tpr = 4;
     int g1 = 1;
+    int minb = 5;      // resident CTAs per SM the SELL kernel is compiled for
 };
 
 static inline int launch_k1(const Mat& A, const PcgDev* dev, const double* p, double* q, double* part_pq,
               cudaStream_t st) {
     if (A.sell) {
-        pcg_spmv_dot_sell_kernel<<<A.g1, PCG_THREADS, 0, st>>>(dev, A.n, A.sell->nslices,
-                                                               A.sell->slice_w, A.sell->cols,
-                                                               A.sell->vals, p, q, part_pq);
+#define GOS(M)                                                                                 \
+    pcg_spmv_dot_sell_kernel<M><<<A.g1, PCG_THREADS, 0, st>>>(dev, A.n, A.sell->nslices,       \
+                                                              A.sell->slice_w, A.sell->cols,   \
+                                                              A.sell->vals, p, q, part_pq)
+        switch (A.minb) {
+            case 5: GOS(5); break;
+            case 6: GOS(6); break;
+            default: GOS(4); break;
+        }
+#undef GOS
     } else {
 #define GO(T)                                                                                  \
     pcg_spmv_dot_csr_kernel<T><<<A.g1, PCG_THREADS, 0, st>>>(dev, A.n, A.indptr, A.indices,    \

@@ -190,7 +190,7 @@ int sell_from_csr(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
 }
 
 // y = A x, one warp per slice, grid-stride over slices.
-__global__ void __launch_bounds__(SPMV_THREADS, 4)
+__global__ void __launch_bounds__(SPMV_THREADS, 5)
 sell_spmv_kernel(int32_t n, int32_t nslices, const u32* __restrict__ slice_w,
                  const int32_t* __restrict__ cols, const double* __restrict__ vals,
                  const double* __restrict__ x, double* __restrict__ y) {
@@ -228,7 +228,7 @@ extern "C" int nodal_sell_spmv(nodal_ctx* ctx, const nodal_sell* m, const double
     if (m->n == 0) return NODAL_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t want = ((int64_t)m->nslices * 32 + SPMV_THREADS - 1) / SPMV_THREADS;
-    const int64_t cap = (int64_t)ctx->num_sms * 4;
+    const int64_t cap = (int64_t)ctx->num_sms * 5;
     sell_spmv_kernel<<<(int)(want < cap ? want : cap), SPMV_THREADS, 0, (cudaStream_t)stream>>>(
         m->n, m->nslices, m->slice_w, m->cols, m->vals, x, y);
     KERNEL_CHECK();

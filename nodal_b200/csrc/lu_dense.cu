@@ -220,16 +220,25 @@ lu_trsm_kernel(double* __restrict__ A, int n, int k, int jb) {
 
 // ---------------------------------------------------------------- DMMA trailing update
 // C[M x N] -= Amat[M x K] * Bmat[K x N], all row-major with leading dimension ld.
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 32;
+constexpr int GM_BM = 128, GM_BK = 32;
 constexpr int GM_THREADS = 256;
 constexpr int GM_LDA = GM_BK + 4;    // 36: (row * 36 + col) hits 16 distinct 8-byte banks per half warp
-constexpr int GM_LDB = GM_BN + 4;    // 132
-constexpr int GM_STAGE = GM_BM * GM_LDA + GM_BK * GM_LDB;   // doubles per stage
+template <int TN> struct GemmCfg {
+    static constexpr int BN = 16 * TN;                 // 2 warps across N, TN 8-column groups each
+    static constexpr int LDB = BN + 4;                 // same bank argument for the B fragments
+    static constexpr int STAGE = GM_BM * GM_LDA + GM_BK * LDB;   // doubles per stage
+    static constexpr int MINB = TN <= 4 ? 2 : 1;       // CTAs per SM the register budget allows
+};
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
     const int bytes = pred ? 8 : 0;   // src-size 0 -> zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src, bool pred) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int bytes = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(src), "r"(bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -241,39 +250,56 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1)
+// C[M x N] -= Amat[M x K] * Bmat[K x N], all row-major with leading dimension ld.
+// 8 warps as 4 (M) x 2 (N); warp tile 32 x (8 TN).  TN = 8: 128 x 128 CTA tile, 1 CTA/SM;
+// TN = 4: 128 x 64 tile, 64 accumulator registers, 2 CTAs/SM (one CTA's barrier / cp.async wait
+// overlaps the other's DMMA).  VEC2: ld and all offsets even -> 16-byte cp.async.
+template <int TN, bool VEC2>
+__global__ void __launch_bounds__(GM_THREADS, GemmCfg<TN>::MINB)
 lu_gemm_kernel(double* __restrict__ C, const double* __restrict__ Amat, const double* __restrict__ Bmat,
                int M, int N, int K, int ld) {
+    using Cfg = GemmCfg<TN>;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;          // 4 x 2 warps, warp tile 32 x 64
-    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * Cfg::BN;
     const int nchunks = (K + GM_BK - 1) / GM_BK;
 
     auto load_chunk = [&](int chunk, int stage) {
-        double* sA = smem + (size_t)stage * GM_STAGE;
+        double* sA = smem + (size_t)stage * Cfg::STAGE;
         double* sB = sA + GM_BM * GM_LDA;
         const int k0 = chunk * GM_BK;
-        // A chunk: 128 rows x 32 k
-        for (int idx = tid; idx < GM_BM * GM_BK; idx += GM_THREADS) {
-            const int r = idx >> 5, c = idx & 31;
-            const bool ok = (m0 + r < M) && (k0 + c < K);
-            cp_async8(&sA[r * GM_LDA + c], ok ? &Amat[(size_t)(m0 + r) * ld + k0 + c] : Amat, ok);
-        }
-        // B chunk: 32 k x 128 cols
-        for (int idx = tid; idx < GM_BK * GM_BN; idx += GM_THREADS) {
-            const int r = idx >> 7, c = idx & 127;
-            const bool ok = (k0 + r < K) && (n0 + c < N);
-            cp_async8(&sB[r * GM_LDB + c], ok ? &Bmat[(size_t)(k0 + r) * ld + n0 + c] : Bmat, ok);
+        if (VEC2) {
+            for (int idx = tid; idx < GM_BM * GM_BK / 2; idx += GM_THREADS) {
+                const int r = idx >> 4, c = (idx & 15) * 2;
+                const bool ok = (m0 + r < M) && (k0 + c < K);
+                cp_async16(&sA[r * GM_LDA + c], ok ? &Amat[(size_t)(m0 + r) * ld + k0 + c] : Amat, ok);
+            }
+            for (int idx = tid; idx < GM_BK * Cfg::BN / 2; idx += GM_THREADS) {
+                const int r = idx / (Cfg::BN / 2), c = (idx % (Cfg::BN / 2)) * 2;
+                const bool ok = (k0 + r < K) && (n0 + c < N);
+                cp_async16(&sB[r * Cfg::LDB + c], ok ? &Bmat[(size_t)(k0 + r) * ld + n0 + c] : Bmat, ok);
+            }
+        } else {
+            for (int idx = tid; idx < GM_BM * GM_BK; idx += GM_THREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                const bool ok = (m0 + r < M) && (k0 + c < K);
+                cp_async8(&sA[r * GM_LDA + c], ok ? &Amat[(size_t)(m0 + r) * ld + k0 + c] : Amat, ok);
+            }
+            for (int idx = tid; idx < GM_BK * Cfg::BN; idx += GM_THREADS) {
+                const int r = idx / Cfg::BN, c = idx % Cfg::BN;
+                const bool ok = (k0 + r < K) && (n0 + c < N);
+                cp_async8(&sB[r * Cfg::LDB + c], ok ? &Bmat[(size_t)(k0 + r) * ld + n0 + c] : Bmat, ok);
+            }
         }
         cp_async_commit();
     };
 
-    double acc[4][8][2];
+    double acc[4][TN][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     load_chunk(0, 0);
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -284,21 +310,21 @@ lu_gemm_kernel(double* __restrict__ C, const double* __restrict__ Amat, const do
             cp_async_wait<0>();
         }
         __syncthreads();
-        const double* sA = smem + (size_t)(ch & 1) * GM_STAGE;
+        const double* sA = smem + (size_t)(ch & 1) * Cfg::STAGE;
         const double* sB = sA + GM_BM * GM_LDA;
 #pragma unroll
         for (int kk = 0; kk < GM_BK; kk += 4) {
-            double af[4], bf[8];
+            double af[4], bf[TN];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 af[i] = sA[(wm * 32 + i * 8 + (lane >> 2)) * GM_LDA + kk + (lane & 3)];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                bf[j] = sB[(kk + (lane & 3)) * GM_LDB + wn * 64 + j * 8 + (lane >> 2)];
+            for (int j = 0; j < TN; ++j)
+                bf[j] = sB[(kk + (lane & 3)) * Cfg::LDB + wn * (8 * TN) + j * 8 + (lane >> 2)];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < TN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         __syncthreads();
     }
@@ -308,13 +334,34 @@ lu_gemm_kernel(double* __restrict__ C, const double* __restrict__ Amat, const do
         const int r = m0 + wm * 32 + i * 8 + (lane >> 2);
         if (r >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = n0 + wn * 64 + j * 8 + (lane & 3) * 2;
+        for (int j = 0; j < TN; ++j) {
+            const int c = n0 + wn * (8 * TN) + j * 8 + (lane & 3) * 2;
             double* p = &C[(size_t)r * ld + c];
-            if (c < N) p[0] -= acc[i][j][0];
-            if (c + 1 < N) p[1] -= acc[i][j][1];
+            if (VEC2) {
+                if (c + 1 < N) {
+                    double2 v = *reinterpret_cast<double2*>(p);
+                    v.x -= acc[i][j][0]; v.y -= acc[i][j][1];
+                    *reinterpret_cast<double2*>(p) = v;
+                } else if (c < N) {
+                    p[0] -= acc[i][j][0];
+                }
+            } else {
+                if (c < N) p[0] -= acc[i][j][0];
+                if (c + 1 < N) p[1] -= acc[i][j][1];
+            }
         }
     }
+}
+
+template <int TN, bool VEC2>
+static int launch_gemm(double* C, const double* A, const double* B, int M, int N, int K, int ld, cudaStream_t st) {
+    using Cfg = GemmCfg<TN>;
+    const size_t smem = sizeof(double) * 2 * (size_t)Cfg::STAGE;
+    CUDA_TRY(cudaFuncSetAttribute(lu_gemm_kernel<TN, VEC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((N + Cfg::BN - 1) / Cfg::BN, (M + GM_BM - 1) / GM_BM);
+    lu_gemm_kernel<TN, VEC2><<<grid, GM_THREADS, smem, st>>>(C, A, B, M, N, K, ld);
+    KERNEL_CHECK();
+    return NODAL_OK;
 }
 
 // ---------------------------------------------------------------- solve phase
@@ -409,12 +456,10 @@ extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double
     CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
 
     const size_t trsm_smem = sizeof(double) * ((size_t)LU_NB * PANEL_LD + (size_t)LU_NB * TRSM_COLS);
-    const size_t gemm_smem = sizeof(double) * 2 * (size_t)GM_STAGE;
     const size_t trsv_smem = sizeof(double) * ((size_t)LU_NB * PANEL_LD + LU_NB);
     {
         CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
-        CUDA_TRY(cudaFuncSetAttribute(lu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
         CUDA_TRY(cudaFuncSetAttribute(lu_trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv_smem));
         CUDA_TRY(cudaFuncSetAttribute(lu_apply_pivots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
@@ -440,11 +485,19 @@ extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double
         if (rest > 0) {
             lu_trsm_kernel<<<(rest + TRSM_COLS - 1) / TRSM_COLS, TRSM_THREADS, trsm_smem, st>>>(G, n, k, jb);
             KERNEL_CHECK();
-            dim3 grid((rest + GM_BN - 1) / GM_BN, (rest + GM_BM - 1) / GM_BM);
-            lu_gemm_kernel<<<grid, GM_THREADS, gemm_smem, st>>>(
-                G + (size_t)(k + jb) * n + (k + jb), G + (size_t)(k + jb) * n + k,
-                G + (size_t)k * n + (k + jb), rest, rest, jb, n);
-            KERNEL_CHECK();
+            double* Cp = G + (size_t)(k + jb) * n + (k + jb);
+            const double* Ap = G + (size_t)(k + jb) * n + k;
+            const double* Bp = G + (size_t)k * n + (k + jb);
+            // all offsets are even when n is even (k, jb are multiples of 2): 16-byte copies
+            const bool vec2 = (n % 2 == 0) && (((uintptr_t)G & 15) == 0) && (jb % 2 == 0);
+            const int tn = getenv("NODAL_LU_GEMM_TN") ? atoi(getenv("NODAL_LU_GEMM_TN")) : 4;
+            if (tn == 8) {
+                if (vec2) NODAL_TRY((launch_gemm<8, true>(Cp, Ap, Bp, rest, rest, jb, n, st)));
+                else NODAL_TRY((launch_gemm<8, false>(Cp, Ap, Bp, rest, rest, jb, n, st)));
+            } else {
+                if (vec2) NODAL_TRY((launch_gemm<4, true>(Cp, Ap, Bp, rest, rest, jb, n, st)));
+                else NODAL_TRY((launch_gemm<4, false>(Cp, Ap, Bp, rest, rest, jb, n, st)));
+            }
         }
     }
     int* info_pinned = reinterpret_cast<int*>(ctx->pinned);

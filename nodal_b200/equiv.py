@@ -1,61 +1,65 @@
-"""`nodal-resistance FILE [-s]` and equivalent_resistance() (mirror of reference nodal/equiv.py)."""
-import argparse
-from copy import deepcopy
+"""`nodal-resistance FILE [-s]` and equivalent_resistance().
+
+Mirror of the reference's nodal/equiv.py: same function signature, same errors, same command
+line; the probe-source solve runs on the GPU.
+"""
+import copy
+import sys
 
 import nodal_b200 as n
+from nodal_b200.cli import load_netlist_or_exit, make_parser
 
-parser = argparse.ArgumentParser(
-    description="Calculate equivalent resistance using nodal analysis"
-    "\n"
-    "Label nodes as '1' and 'g' to mark where to connect to the network.")
-parser.add_argument("netlist_path", metavar="FILE", help="csv file describing the resistive network")
-parser.add_argument("-s", "--sparse", action="store_true", help="use a sparse matrix")
+parser = make_parser(
+    "Calculate equivalent resistance using nodal analysis\n"
+    "Label nodes as '1' and 'g' to mark where to connect to the network.",
+    "csv file describing the resistive network")
+
+PROBE = ("a1", "A", "1")          # name, type, value of the 1 A source the method inserts (equiv.py:51)
 
 
 def check_resistive(netlist):
-    """True when every component of the netlist is a resistor (equiv.py:22-28)."""
+    """True when the netlist contains resistors only (reference equiv.py:22-28)."""
     return netlist.is_resistive()
 
 
 def equivalent_resistance(netlist, a, b, sparse=False, **options):
-    """Equivalent resistance seen through nodes a and b (equiv.py:31-61).
+    """Resistance seen between nodes `a` and `b` (reference equiv.py:31-61).
 
-    A 1 A source is connected from b to a, the circuit is solved on the GPU and
-    R = e(a) - e(b).  Raises ValueError for non-resistive netlists and KeyError
-    for unknown nodes.  `options` are forwarded to Circuit (rtol, maxit, ...).
+    Method: connect a 1 A current source from b to a, solve, return e(a) - e(b).
+    Raises ValueError if anything but resistors is present and KeyError if a or b is not a
+    node of the netlist.  Extra keyword `options` go to Circuit (rtol, maxit, ...).
     """
     if not check_resistive(netlist):
         raise ValueError("Network is not resistive")
-    for node in (a, b):
-        if node not in netlist.nodenum and node != netlist.ground:
-            raise KeyError(f"Node `{node}` not found in netlist")
-    probe = deepcopy(netlist)
-    probe.process_component(["a1", "A", "1", a, b])
-    solution = n.Circuit(probe, sparse=sparse, **options).solve()
-    e = [0, 0]
-    for k, node in enumerate((a, b)):
-        if node != "g":          # literal "g", as the reference (equiv.py:57)
-            e[k] = solution.result[solution.nodenum[node]]
+    missing = [node for node in (a, b) if node != netlist.ground and node not in netlist.nodenum]
+    if missing:
+        raise KeyError(f"Node `{missing[0]}` not found in netlist")
+
+    probed = copy.deepcopy(netlist)                      # the caller's netlist stays untouched
+    probed.process_component([*PROBE, a, b])
+    solution = n.Circuit(probed, sparse=sparse, **options).solve()
     equivalent_resistance.last_stats = solution.stats
-    return e[0] - e[1]
+
+    def potential(node):
+        # the reference tests against the literal "g", not netlist.ground (equiv.py:57)
+        return 0 if node == "g" else solution.result[solution.nodenum[node]]
+
+    return potential(a) - potential(b)
 
 
 def main(argv=None):
-    args = parser.parse_args(argv)
+    options = parser.parse_args(argv)
+    netlist = load_netlist_or_exit(options.netlist_path)
     try:
-        netlist = n.Netlist(args.netlist_path)
-    except FileNotFoundError:
-        exit(1)
-    try:
-        r = equivalent_resistance(netlist, "1", "g", sparse=args.sparse)
+        r = equivalent_resistance(netlist, "1", "g", sparse=options.sparse)
     except ValueError:
         print("Invalid netlist\n")
         print("Resistors are the only component allowed in the circuit")
-        exit(1)
-    except KeyError as e:
+        sys.exit(1)
+    except KeyError as err:
         print("Invalid netlist\n")
-        print(e.args[0])
-        exit(1)
+        print(err.args[0])
+        sys.exit(1)
     print(f"R = {r}")
 
 

@@ -1,24 +1,30 @@
-"""Command line entry `nodal-solver FILE [-s]` (mirror of reference nodal/solver.py:1-35)."""
-import argparse
+"""`nodal-solver FILE [-s]`: print every node potential and branch current of a netlist.
+
+Mirror of the reference's nodal/solver.py (same arguments, same exit codes, same output); the
+solve itself runs on the GPU through nodal_b200.Circuit.
+"""
+import sys
 
 import nodal_b200 as n
+from nodal_b200.cli import load_netlist_or_exit, make_parser
 
-parser = argparse.ArgumentParser(description="Solve electrical circuits using nodal analysis")
-parser.add_argument("netlist_path", metavar="FILE", help="csv file describing the netlist")
-parser.add_argument("-s", "--sparse", action="store_true", help="use a sparse matrix")
+parser = make_parser("Solve electrical circuits using nodal analysis", "csv file describing the netlist")
+
+
+def solve_file(path, sparse=False):
+    """Returns the printable Solution, or None when the circuit has floating nodes."""
+    netlist = load_netlist_or_exit(path)
+    try:
+        return n.Circuit(netlist, sparse=sparse).solve()
+    except n.UnconnectedCircuitError:
+        return None
 
 
 def main(argv=None):
-    args = parser.parse_args(argv)
-    try:
-        netlist = n.Netlist(args.netlist_path)
-    except FileNotFoundError:
-        exit(1)
-    circuit = n.Circuit(netlist, sparse=args.sparse)
-    try:
-        solution = circuit.solve()
-    except n.UnconnectedCircuitError:
-        exit(1)
+    options = parser.parse_args(argv)
+    solution = solve_file(options.netlist_path, sparse=options.sparse)
+    if solution is None:
+        sys.exit(1)
     print(solution)
 
 

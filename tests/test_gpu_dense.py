@@ -225,3 +225,26 @@ def test_sparse_singular_returns_nan_like_reference(device, tmp_path):
         assert np.linalg.norm(G @ sol.result - A) <= 1e-9 * np.linalg.norm(A)
     else:
         assert np.isnan(sol.result).all() or sol.stats["status"] == 2
+
+
+def test_cli_end_to_end(device, tmp_path, capsys):
+    """`nodal-solver FILE [-s]` and `nodal-resistance FILE [-s]` print what the reference prints."""
+    from nodal_b200 import equiv, solver
+    path = write_csv(DOC["1.6.1.csv"]["rows"], tmp_path / "c1.csv")
+    for flags in ([], ["-s"]):
+        solver.main([path] + flags)
+        lines = capsys.readouterr().out.strip().splitlines()
+        ref = PINNED["printed"]["1.6.1.csv"].splitlines()
+        assert lines[0] == ref[0] and [l.split(" \t= ")[0] for l in lines] == [l.split(" \t= ")[0] for l in ref]
+        got = [float(l.split("= ")[1]) for l in lines[1:]]
+        exp = [float(l.split("= ")[1]) for l in ref[1:]]
+        assert block_err(got, exp, 3) < 1e-9
+    path = write_csv(DOC["resistive_3.csv"]["rows"], tmp_path / "r3.csv")
+    for flags in ([], ["-s"]):
+        equiv.main([path] + flags)
+        out = capsys.readouterr().out.strip()
+        assert out.startswith("R = ") and float(out[4:]) == pytest.approx(1.0, rel=1e-9)
+    path = write_csv(DOC["unconnected_1.csv"]["rows"], tmp_path / "u1.csv")
+    with pytest.raises(SystemExit) as e:
+        solver.main([path])
+    assert e.value.code == 1

@@ -216,3 +216,27 @@ def test_no_silent_cpu_fallback(tmp_path):
     net = n.Netlist(write_csv(DOC["1.6.1.csv"]["rows"], tmp_path / "a.csv"))
     with pytest.raises(NodalLibraryError):
         n.Circuit(net)
+
+
+def test_cli_error_paths_without_gpu(tmp_path, capsys):
+    """Exit codes / messages of the two console scripts (reference solver.py:19-29, equiv.py:69-83)."""
+    from nodal_b200 import equiv, solver
+    with pytest.raises(SystemExit) as e:
+        solver.main([str(tmp_path / "missing.csv")])
+    assert e.value.code == 1
+    with pytest.raises(SystemExit) as e:
+        equiv.main([str(tmp_path / "missing.csv"), "-s"])
+    assert e.value.code == 1
+    path = write_csv(DOC["1.6.1.csv"]["rows"], tmp_path / "nr.csv")
+    with pytest.raises(SystemExit) as e:
+        equiv.main([path])
+    assert e.value.code == 1
+    out = capsys.readouterr().out
+    assert "Invalid netlist" in out and "Resistors are the only component allowed" in out
+    path = write_csv([["r1", "R", "1", "a", "b"], ["r2", "R", "1", "b", "c"]], tmp_path / "nonode.csv")
+    with pytest.raises(SystemExit) as e:
+        equiv.main([path])
+    assert e.value.code == 1
+    assert "not found in netlist" in capsys.readouterr().out
+    assert solver.parser.parse_args(["x.csv", "-s"]).sparse is True
+    assert equiv.parser.parse_args(["x.csv"]).sparse is False

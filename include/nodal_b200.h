@@ -144,6 +144,36 @@ int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
                 double rtol, int32_t restart, int32_t maxit,
                 int32_t* iters_h, double* relres_h, void* stream);
 
+/* ---------------------------------------------------------------- AMG-preconditioned CG (opt-in)
+ * Alternative to nodal_pcg for the same call site (`spsolve(G, A)`, nodal/nodal.py:325) on
+ * symmetric positive definite systems: a V(1,1) cycle over pairwise aggregates (csrc/amg.cu)
+ * replaces the Jacobi preconditioner, so the iteration count stays nearly flat in n.
+ *
+ * nodal_amg_create builds the hierarchy for the CSR matrix (device pointers; the arrays must
+ * stay alive and unchanged until nodal_amg_destroy).  params is NULL or 8 doubles, 0 = default:
+ * [0] pairwise passes per level (2), [1] stop coarsening at this many rows (512), [2] Jacobi
+ * damping (0.8), [3] coarse-correction scale (1.8), [4] max levels (30), [5] handshake rounds
+ * (8), [6] largest coarsest level that is inverted explicitly (2048), [7] reserved.
+ * nodal_amg_info: level count, rows / nnz per level (up to cap entries), setup time, whether the
+ * coarsest level is solved exactly.  nodal_amg_fetch_level copies a level's aggregate map
+ * (agg, n entries; not on the coarsest level) and/or CSR arrays to device buffers (NULL = skip).
+ * nodal_amg_apply: z = M r, one cycle.  nodal_amg_pcg: solve A x = rhs starting from x;
+ * status / iters_h / relres_h as nodal_pcg (relres is the true residual); stats_h (16 doubles or
+ * NULL): [0] levels, [1] operator complexity, [2] restarts, [3] solve ms, [4] setup ms,
+ * [5] rows of the coarsest level, [6] grid complexity, [7] coarsest level solved exactly. */
+typedef struct nodal_amg nodal_amg;
+int nodal_amg_create(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+                     const int32_t* indices, const double* data, const double* params,
+                     nodal_amg** out, void* stream);
+int nodal_amg_destroy(nodal_amg* amg);
+int nodal_amg_info(const nodal_amg* amg, int32_t cap, int32_t* nlevels, int64_t* rows, int64_t* nnz,
+                   double* setup_ms, int32_t* direct);
+int nodal_amg_fetch_level(nodal_ctx* ctx, const nodal_amg* amg, int32_t level, int32_t* agg,
+                          int32_t* indptr, int32_t* indices, double* data, void* stream);
+int nodal_amg_apply(nodal_ctx* ctx, const nodal_amg* amg, const double* r, double* z, void* stream);
+int nodal_amg_pcg(nodal_ctx* ctx, nodal_amg* amg, const double* rhs, double* x, double rtol,
+                  int32_t maxit, int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
+
 /* ---------------------------------------------------------------- dense kernels
  * Blocked FP64 LU with partial pivoting + triangular solves.  Replaces
  * numpy.linalg.solve (LAPACK dgesv) at nodal/nodal.py:327.  G (n x n row-major)

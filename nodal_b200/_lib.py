@@ -39,6 +39,14 @@ SIGNATURES = {
                             C.POINTER(_i32), C.POINTER(_f64), C.POINTER(_f64), _vp]),
     "nodal_gmres": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _i32,
                               C.POINTER(_i32), C.POINTER(_f64), _vp]),
+    "nodal_amg_create": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, C.POINTER(_f64), C.POINTER(_vp), _vp]),
+    "nodal_amg_destroy": (C.c_int, [_vp]),
+    "nodal_amg_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64),
+                                 C.POINTER(_f64), C.POINTER(_i32)]),
+    "nodal_amg_fetch_level": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "nodal_amg_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "nodal_amg_pcg": (C.c_int, [_vp, _vp, _vp, _vp, _f64, _i32, C.POINTER(_i32), C.POINTER(_f64),
+                                C.POINTER(_f64), _vp]),
     "nodal_lu_solve": (C.c_int, [_vp, _i32, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
     "nodal_lu_batched": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _i32, _i32, _vp, _vp, _vp, _vp]),

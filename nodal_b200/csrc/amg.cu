@@ -1,0 +1,790 @@
+// Aggregation AMG preconditioner + preconditioned CG in FP64 (opt-in alternative to the
+// Jacobi-PCG of pcg.cu for the `spsolve(G, A)` call, nodal/nodal.py:325, on R / A netlists).
+//
+// Why: Jacobi-PCG needs O(sqrt(n)) iterations on grid-like networks (18 741 on the 4096 x 4096
+// grid); a V-cycle over pairwise aggregates keeps the count nearly flat (31 .. 45 from 128^2 to
+// 1024^2 in the numpy statement of this algorithm, tests/amg_mirror.py).
+//
+// Setup, per level (everything on the device, deterministic, no floating-point atomics):
+//   * two passes of pairwise aggregation (Notay-style double pairwise): a handshake matching --
+//     every unmatched row proposes to its preferred unmatched neighbour (amg_core.cuh), mutual
+//     proposals become pairs, 8 rounds -- then rows left alone join the pair of their preferred
+//     neighbour;
+//   * aggregate ids = exclusive scan over the "I am the smallest index of my aggregate" flags;
+//   * Galerkin operator P^T A P with piecewise-constant P: relabel every stored entry to
+//     (agg[row], agg[col]) and hand the triples to the CSR builder the assembly path uses
+//     (radix sort + in-order segmented sum, csr.cu), so coarse operators are bit-reproducible;
+//   * P^T as a CSR pattern (same builder) so the restriction is a gather, not a scatter.
+// Cycle: V(1,1) with damped Jacobi (omega), coarse correction scaled by `scale` (piecewise-
+// constant prolongation under-corrects smooth error; 1.8 halves the iteration count), the
+// coarsest operator (<= 512 rows by default) is inverted explicitly once (Gauss-Jordan) and
+// applied as a dense mat-vec.  All operators are stored as SELL-32 (sparse.cuh).
+#include <algorithm>
+#include <cmath>
+
+#include "amg_core.cuh"
+#include "sparse.cuh"
+
+constexpr int AT = 256;
+
+// ------------------------------------------------------------------ setup kernels
+#define ROW_LOOP(i, n)                                                              \
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)(n); \
+         i += (int64_t)gridDim.x * blockDim.x)
+
+__global__ void __launch_bounds__(AT)
+amg_propose_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const double* __restrict__ data, const int32_t* __restrict__ match,
+                   int32_t* __restrict__ best) {
+    ROW_LOOP(i, n) best[i] = match[i] >= 0 ? -1 : amg_pick((int32_t)i, indptr, indices, data, match);
+}
+
+__global__ void __launch_bounds__(AT)
+amg_accept_kernel(int32_t n, const int32_t* __restrict__ best, int32_t* __restrict__ match) {
+    ROW_LOOP(i, n) {
+        if (match[i] >= 0) continue;
+        const int32_t b = best[i];
+        if (b >= 0 && best[b] == (int32_t)i) match[i] = b;
+    }
+}
+
+__global__ void __launch_bounds__(AT)
+amg_root_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const double* __restrict__ data, const int32_t* __restrict__ match,
+                int32_t* __restrict__ root, u32* __restrict__ leader) {
+    ROW_LOOP(i, n) {
+        const int32_t r = amg_root((int32_t)i, indptr, indices, data, match);
+        root[i] = r;
+        leader[i] = r == (int32_t)i ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(AT)
+amg_assign_kernel(int32_t n, const int32_t* __restrict__ root, const u32* __restrict__ ids,
+                  int32_t* __restrict__ agg) {
+    ROW_LOOP(i, n) agg[i] = (int32_t)ids[root[i]];
+}
+
+__global__ void __launch_bounds__(AT)
+amg_compose_kernel(int32_t n, int32_t* __restrict__ comp, const int32_t* __restrict__ next) {
+    ROW_LOOP(i, n) comp[i] = next[comp[i]];
+}
+
+__global__ void __launch_bounds__(AT)
+amg_relabel_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const double* __restrict__ data, const int32_t* __restrict__ agg, int cb,
+                   u64* __restrict__ keys, double* __restrict__ vals) {
+    ROW_LOOP(i, n) {
+        const u64 hi = (u64)agg[i] << cb;
+        const int32_t e = indptr[i + 1];
+        for (int32_t p = indptr[i]; p < e; ++p) {
+            keys[p] = hi | (u64)agg[indices[p]];
+            vals[p] = data[p];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(AT)
+amg_pt_keys_kernel(int32_t n, const int32_t* __restrict__ agg, int cb, u64* __restrict__ keys,
+                   double* __restrict__ vals) {
+    ROW_LOOP(i, n) {
+        keys[i] = ((u64)agg[i] << cb) | (u64)i;
+        vals[i] = 1.0;
+    }
+}
+
+// ------------------------------------------------------------------ coarsest level: explicit inverse
+// [A | I] -> [I | A^-1] by Gauss-Jordan without pivoting (A is symmetric positive definite),
+// one launch per pivot, ping-pong between two n x 2n buffers so a step has no read/write race.
+__global__ void __launch_bounds__(AT)
+amg_dense_init_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                      const double* __restrict__ data, double* __restrict__ M) {
+    const int64_t W = 2 * (int64_t)n;
+    ROW_LOOP(i, n) {
+        M[i * W + n + i] = 1.0;
+        const int32_t e = indptr[i + 1];
+        for (int32_t p = indptr[i]; p < e; ++p) M[i * W + indices[p]] = data[p];
+    }
+}
+
+__global__ void __launch_bounds__(AT)
+amg_gj_step_kernel(int32_t n, int32_t k, const double* __restrict__ src, double* __restrict__ dst,
+                   int* __restrict__ bad) {
+    const int64_t W = 2 * (int64_t)n;
+    const double piv = src[k * W + k];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !(piv > 0.0) && *bad == 0) *bad = k + 1;
+    ROW_LOOP(idx, (int64_t)n * W) {
+        const int64_t i = idx / W, j = idx - i * W;
+        const double rkj = src[k * W + j] / piv;
+        dst[idx] = i == k ? rkj : src[idx] - src[i * W + k] * rkj;
+    }
+}
+
+__global__ void __launch_bounds__(AT)
+amg_dense_extract_kernel(int32_t n, const double* __restrict__ M, double* __restrict__ inv) {
+    const int64_t W = 2 * (int64_t)n;
+    ROW_LOOP(idx, (int64_t)n * n) {
+        const int64_t i = idx / n, j = idx - i * n;
+        inv[idx] = M[i * W + n + j];
+    }
+}
+
+// x = inv b, one warp per row
+__global__ void __launch_bounds__(AT)
+amg_gemv_kernel(int32_t n, const double* __restrict__ inv, const double* __restrict__ b,
+                double* __restrict__ x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        double acc = 0.0;
+        for (int32_t j = lane; j < n; j += 32) acc = fma(inv[r * n + j], b[j], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) x[r] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ cycle kernels
+__global__ void __launch_bounds__(AT)
+amg_jacobi0_kernel(int32_t n, const double* __restrict__ dinv, const double* __restrict__ b,
+                   double omega, double* __restrict__ x) {
+    ROW_LOOP(i, n) x[i] = omega * dinv[i] * b[i];
+}
+
+// SELL-32 sweep, one warp per slice.
+//   MODE 0: y = A x, per-block partial sums of x.y        (CG: q = A p, p.q)
+//   MODE 1: y = b - A x                                   (residual)
+//   MODE 2: y = x + omega D^-1 (b - A x)                  (damped Jacobi sweep, out of place)
+template <int MODE>
+__global__ void __launch_bounds__(AT, 4)
+amg_sell_kernel(int32_t n, int32_t nslices, const u32* __restrict__ slice_w,
+                const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                const double* __restrict__ dinv, const double* __restrict__ b,
+                const double* __restrict__ x, double omega, double* __restrict__ y,
+                double* __restrict__ part) {
+    __shared__ double red[33];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int64_t s = warp; s < nslices; s += nwarps) {
+        const u32 w0 = slice_w[s];
+        const int w = (int)(slice_w[s + 1] - w0);
+        const double acc = sell_row_dot(cols, vals, (int64_t)w0 * 32 + lane, w, x);
+        const int64_t r = s * 32 + lane;
+        if (r < n) {
+            if (MODE == 0) { y[r] = acc; dot = fma(x[r], acc, dot); }
+            if (MODE == 1) y[r] = b[r] - acc;
+            if (MODE == 2) y[r] = x[r] + omega * dinv[r] * (b[r] - acc);
+        }
+    }
+    if (MODE == 0) {
+        const double t = block_sum(dot, red);
+        if (threadIdx.x == 0) part[blockIdx.x] = t;
+    }
+}
+
+// bc[I] = sum of r over the members of aggregate I, in increasing row order
+__global__ void __launch_bounds__(AT)
+amg_restrict_kernel(int32_t nc, const int32_t* __restrict__ pt_ptr, const int32_t* __restrict__ pt_idx,
+                    const double* __restrict__ r, double* __restrict__ bc) {
+    ROW_LOOP(I, nc) {
+        double s = 0.0;
+        const int32_t e = pt_ptr[I + 1];
+        for (int32_t p = pt_ptr[I]; p < e; ++p) s += r[pt_idx[p]];
+        bc[I] = s;
+    }
+}
+
+__global__ void __launch_bounds__(AT)
+amg_prolong_kernel(int32_t n, const int32_t* __restrict__ agg, const double* __restrict__ xc,
+                   double scale, const double* __restrict__ x, double* __restrict__ xa) {
+    ROW_LOOP(i, n) xa[i] = x[i] + scale * xc[agg[i]];
+}
+
+// ------------------------------------------------------------------ CG vector kernels
+__global__ void __launch_bounds__(AT)
+apcg_dot_kernel(int32_t n, const double* __restrict__ a, const double* __restrict__ b,
+                double* __restrict__ part) {
+    __shared__ double red[33];
+    double t = 0.0;
+    ROW_LOOP(i, n) t = fma(a[i], b[i], t);
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(AT)
+apcg_sum_kernel(const double* __restrict__ part, int count, double* __restrict__ out) {
+    __shared__ double red[33];
+    const double t = reduce_partials(part, count, red);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
+// alpha = rz / p.q ; x += alpha p ; r -= alpha q ; partial sums of r.r
+__global__ void __launch_bounds__(AT)
+apcg_update_kernel(int32_t n, const double* __restrict__ part_pq, int npq, const double* __restrict__ rz,
+                   const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
+                   double* __restrict__ r, double* __restrict__ part_rr) {
+    __shared__ double red[33];
+    const double pq = reduce_partials(part_pq, npq, red);
+    const double alpha = rz[0] / pq;
+    double t = 0.0;
+    ROW_LOOP(i, n) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        t = fma(ri, ri, t);
+    }
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) part_rr[blockIdx.x] = t;
+}
+
+// rz' = r.z (from partials) ; beta = rz'/rz ; p = z + beta p
+__global__ void __launch_bounds__(AT)
+apcg_direction_kernel(int32_t n, const double* __restrict__ part_rz, int nrz,
+                      const double* __restrict__ rz_old, double* __restrict__ rz_new,
+                      const double* __restrict__ z, double* __restrict__ p, int first) {
+    __shared__ double red[33];
+    const double rzn = reduce_partials(part_rz, nrz, red);
+    const double beta = first ? 0.0 : rzn / rz_old[0];
+    ROW_LOOP(i, n) p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) rz_new[0] = rzn;
+}
+
+// ------------------------------------------------------------------ host side
+struct AmgLevel {
+    int32_t n = 0;
+    int64_t nnz = 0;
+    const int32_t* indptr = nullptr;    // CSR of the level operator (level 0: the caller's arrays)
+    const int32_t* indices = nullptr;
+    const double* data = nullptr;
+    bool owned = false;
+    nodal_sell* sell = nullptr;
+    int32_t nc = 0;                     // rows of the next level (0 on the coarsest)
+    int32_t* agg = nullptr;             // [n]  row -> aggregate
+    int32_t* pt_ptr = nullptr;          // [>= nc + 1]  members of every aggregate ...
+    int32_t* pt_idx = nullptr;          // [n]          ... in increasing row order
+    double *b = nullptr, *x = nullptr, *r = nullptr;   // cycle work vectors (b: levels > 0)
+};
+
+struct nodal_amg {
+    nodal_ctx* ctx = nullptr;
+    int device = 0;
+    int passes = 2, coarse = 512, maxlevels = 30, rounds = 8, direct_max = 2048;
+    double omega = 0.8, scale = 1.8;
+    std::vector<AmgLevel> lv;           // lv.back() is the coarsest level
+    double* inv = nullptr;              // [nL x nL] inverse of the coarsest operator (or nullptr)
+    double *p = nullptr, *q = nullptr, *r = nullptr, *z = nullptr;   // CG vectors
+    double* part = nullptr;             // 3 x nparts partial sums + scalars
+    int nparts = 0;
+    float setup_ms = 0.f;
+};
+
+namespace {
+
+int rows_grid(const nodal_ctx* ctx, int64_t work) {
+    int64_t b = (work + AT - 1) / AT;
+    const int64_t cap = (int64_t)ctx->num_sms * 16;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+int sell_grid(const nodal_ctx* ctx, int32_t nslices) {
+    int64_t b = ((int64_t)nslices * 32 + AT - 1) / AT;
+    const int64_t cap = (int64_t)ctx->num_sms * 4;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+int bit_length(int64_t v) {
+    int b = 1;
+    while ((v >> b) != 0) ++b;
+    return b;
+}
+
+template <typename T>
+T* pool(nodal_ctx* ctx, size_t count) {
+    T* p = static_cast<T*>(ctx_pool_alloc(ctx, sizeof(T) * (count ? count : 1)));
+    if (!p) nodal_set_error("amg: out of device memory (%zu bytes)", sizeof(T) * count);
+    return p;
+}
+#define POOL(var, type, count)                       \
+    type* var = pool<type>(ctx, (size_t)(count));    \
+    if (!var) return NODAL_CUDA_ERROR
+
+struct Csr {
+    int32_t n = 0;
+    int64_t nnz = 0;
+    const int32_t* indptr = nullptr;
+    const int32_t* indices = nullptr;
+    const double* data = nullptr;
+    bool owned = false;
+};
+void free_csr(nodal_ctx* ctx, Csr& a) {
+    if (a.owned) {
+        ctx_pool_free(ctx, const_cast<int32_t*>(a.indptr));
+        ctx_pool_free(ctx, const_cast<int32_t*>(a.indices));
+        ctx_pool_free(ctx, const_cast<double*>(a.data));
+    }
+    a = Csr();
+}
+
+// One pairwise pass: agg_out[n] (pool) and the number of aggregates.
+int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cudaStream_t st) {
+    nodal_ctx* ctx = h->ctx;
+    const int32_t n = A.n;
+    POOL(match, int32_t, n);
+    POOL(best, int32_t, n);
+    POOL(leader, u32, n);
+    const int grid = rows_grid(ctx, n);
+    CUDA_TRY(cudaMemsetAsync(match, 0xFF, sizeof(int32_t) * (size_t)n, st));
+    for (int r = 0; r < h->rounds; ++r) {
+        amg_propose_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, best);
+        KERNEL_CHECK();
+        amg_accept_kernel<<<grid, AT, 0, st>>>(n, best, match);
+        KERNEL_CHECK();
+    }
+    int32_t* root = best;
+    amg_root_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, root, leader);
+    KERNEL_CHECK();
+    NODAL_TRY(ctx_reserve(ctx, scan_scratch_bytes(n) + 4096));
+    u32* total = carve<u32>(ctx, 16);
+    if (!total) return NODAL_CUDA_ERROR;
+    NODAL_TRY(scan_exclusive_u32(ctx, leader, leader, n, total, st));
+    int32_t* agg = match;
+    amg_assign_kernel<<<grid, AT, 0, st>>>(n, root, leader, agg);
+    KERNEL_CHECK();
+    u32* total_h = reinterpret_cast<u32*>(ctx->pinned);
+    CUDA_TRY(cudaMemcpyAsync(total_h, total, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *nc_out = (int32_t)total_h[0];
+    *agg_out = agg;
+    ctx_pool_free(ctx, best);
+    ctx_pool_free(ctx, leader);
+    return NODAL_OK;
+}
+
+// Ac = P^T A P for the piecewise-constant P of `agg`.
+int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* out, cudaStream_t st) {
+    nodal_ctx* ctx = h->ctx;
+    POOL(keys, u64, A.nnz);
+    POOL(vals, double, A.nnz);
+    POOL(rhs, double, (size_t)nc + 1);
+    const int cb = bit_length(nc);
+    amg_relabel_kernel<<<rows_grid(ctx, A.n), AT, 0, st>>>(A.n, A.indptr, A.indices, A.data, agg, cb,
+                                                         keys, vals);
+    KERNEL_CHECK();
+    int64_t nnzc = 0;
+    NODAL_TRY(nodal_csr_build(ctx, nc, A.nnz, cb, reinterpret_cast<uint64_t*>(keys), vals, rhs, &nnzc, st));
+    POOL(ip, int32_t, (size_t)nc + 1);
+    POOL(ix, int32_t, nnzc);
+    POOL(dv, double, nnzc);
+    NODAL_TRY(nodal_csr_fetch(ctx, nc, nnzc, ip, ix, dv, st));
+    ctx_pool_free(ctx, keys);
+    ctx_pool_free(ctx, vals);
+    ctx_pool_free(ctx, rhs);
+    out->n = nc;
+    out->nnz = nnzc;
+    out->indptr = ip;
+    out->indices = ix;
+    out->data = dv;
+    out->owned = true;
+    return NODAL_OK;
+}
+
+// Members of every aggregate (CSR pattern of P^T), rows in increasing order.
+int transpose_pattern(nodal_amg* h, AmgLevel& L, cudaStream_t st) {
+    nodal_ctx* ctx = h->ctx;
+    const int32_t n = L.n;
+    POOL(keys, u64, n);
+    POOL(vals, double, n);
+    POOL(rhs, double, (size_t)n + 1);
+    const int cb = bit_length(n);
+    amg_pt_keys_kernel<<<rows_grid(ctx, n), AT, 0, st>>>(n, L.agg, cb, keys, vals);
+    KERNEL_CHECK();
+    int64_t cnt = 0;
+    NODAL_TRY(nodal_csr_build(ctx, n, n, cb, reinterpret_cast<uint64_t*>(keys), vals, rhs, &cnt, st));
+    if (cnt != n) {
+        nodal_set_error("amg: internal error, P^T has %lld entries for %d rows", (long long)cnt, n);
+        return NODAL_CUDA_ERROR;
+    }
+    L.pt_ptr = pool<int32_t>(ctx, (size_t)n + 1);
+    L.pt_idx = pool<int32_t>(ctx, n);
+    POOL(ones, double, n);
+    if (!L.pt_ptr || !L.pt_idx) return NODAL_CUDA_ERROR;
+    NODAL_TRY(nodal_csr_fetch(ctx, n, n, L.pt_ptr, L.pt_idx, ones, st));
+    ctx_pool_free(ctx, keys);
+    ctx_pool_free(ctx, vals);
+    ctx_pool_free(ctx, rhs);
+    ctx_pool_free(ctx, ones);
+    return NODAL_OK;
+}
+
+int invert_coarsest(nodal_amg* h, const AmgLevel& L, cudaStream_t st) {
+    nodal_ctx* ctx = h->ctx;
+    const int32_t n = L.n;
+    const size_t elems = (size_t)n * 2 * n;
+    POOL(m0, double, elems + 32);
+    POOL(m1, double, elems);
+    int* bad = reinterpret_cast<int*>(m0 + elems);
+    CUDA_TRY(cudaMemsetAsync(m0, 0, sizeof(double) * (elems + 32), st));
+    amg_dense_init_kernel<<<rows_grid(ctx, n), AT, 0, st>>>(n, L.indptr, L.indices, L.data, m0);
+    KERNEL_CHECK();
+    double *src = m0, *dst = m1;
+    const int grid = rows_grid(ctx, (int64_t)elems);
+    for (int32_t k = 0; k < n; ++k) {
+        amg_gj_step_kernel<<<grid, AT, 0, st>>>(n, k, src, dst, bad);
+        KERNEL_CHECK();
+        std::swap(src, dst);
+    }
+    h->inv = pool<double>(ctx, (size_t)n * n);
+    if (!h->inv) return NODAL_CUDA_ERROR;
+    amg_dense_extract_kernel<<<rows_grid(ctx, (int64_t)n * n), AT, 0, st>>>(n, src, h->inv);
+    KERNEL_CHECK();
+    int* bad_h = reinterpret_cast<int*>(ctx->pinned);
+    CUDA_TRY(cudaMemcpyAsync(bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ctx_pool_free(ctx, m0);
+    ctx_pool_free(ctx, m1);
+    if (*bad_h != 0) {
+        nodal_set_error("amg: the coarsest operator is not positive definite (pivot %d of %d); "
+                        "the matrix is not SPD", *bad_h, n);
+        return NODAL_BREAKDOWN;
+    }
+    return NODAL_OK;
+}
+
+int build_hierarchy(nodal_amg* h, int32_t n, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                    const double* data, cudaStream_t st) {
+    nodal_ctx* ctx = h->ctx;
+    Csr cur;
+    cur.n = n; cur.nnz = nnz; cur.indptr = indptr; cur.indices = indices; cur.data = data;
+    while (cur.n > h->coarse && (int)h->lv.size() < h->maxlevels) {
+        Csr A = cur;            // borrowed view while A is the level operator itself
+        A.owned = false;
+        int32_t* comp = nullptr;
+        for (int pass = 0; pass < h->passes; ++pass) {
+            int32_t* agg = nullptr;
+            int32_t nc = 0;
+            NODAL_TRY(aggregate(h, A, &agg, &nc, st));
+            Csr Ac;
+            NODAL_TRY(galerkin(h, A, agg, nc, &Ac, st));
+            if (!comp) comp = agg;
+            else {
+                amg_compose_kernel<<<rows_grid(ctx, cur.n), AT, 0, st>>>(cur.n, comp, agg);
+                KERNEL_CHECK();
+                ctx_pool_free(ctx, agg);
+            }
+            free_csr(ctx, A);
+            A = Ac;
+        }
+        if ((double)A.n > 0.9 * (double)cur.n) {     // coarsening stalled: cur stays the coarsest
+            free_csr(ctx, A);
+            ctx_pool_free(ctx, comp);
+            break;
+        }
+        AmgLevel L;
+        L.n = cur.n; L.nnz = cur.nnz; L.indptr = cur.indptr; L.indices = cur.indices; L.data = cur.data;
+        L.owned = cur.owned;
+        L.agg = comp;
+        L.nc = A.n;
+        h->lv.push_back(L);
+        NODAL_TRY(transpose_pattern(h, h->lv.back(), st));
+        cur = A;
+    }
+    AmgLevel L;
+    L.n = cur.n; L.nnz = cur.nnz; L.indptr = cur.indptr; L.indices = cur.indices; L.data = cur.data;
+    L.owned = cur.owned;
+    h->lv.push_back(L);
+    for (size_t l = 0; l < h->lv.size(); ++l) {
+        AmgLevel& V = h->lv[l];
+        NODAL_TRY(sell_from_csr(ctx, V.n, V.nnz, V.indptr, V.indices, V.data, &V.sell, st, nullptr));
+        V.x = pool<double>(ctx, V.n);
+        V.r = pool<double>(ctx, V.n);
+        if (l > 0) V.b = pool<double>(ctx, V.n);
+        if (!V.x || !V.r || (l > 0 && !V.b)) return NODAL_CUDA_ERROR;
+    }
+    if (h->lv.back().n <= h->direct_max) NODAL_TRY(invert_coarsest(h, h->lv.back(), st));
+    return NODAL_OK;
+}
+
+template <int MODE>
+int sell_sweep(const nodal_amg* h, const AmgLevel& V, const double* b, const double* x, double* y,
+               double* part, cudaStream_t st) {
+    const nodal_sell* m = V.sell;
+    amg_sell_kernel<MODE><<<sell_grid(h->ctx, m->nslices), AT, 0, st>>>(
+        m->n, m->nslices, m->slice_w, m->cols, m->vals, m->dinv, b, x, h->omega, y, part);
+    KERNEL_CHECK();
+    return NODAL_OK;
+}
+
+// z = M b : one V(1,1) cycle from a zero initial guess
+int cycle(const nodal_amg* h, const double* b0, double* z0, cudaStream_t st) {
+    const nodal_ctx* ctx = h->ctx;
+    const int last = (int)h->lv.size() - 1;
+    for (int l = 0; l < last; ++l) {
+        const AmgLevel& V = h->lv[l];
+        const double* b = l == 0 ? b0 : V.b;
+        amg_jacobi0_kernel<<<rows_grid(ctx, V.n), AT, 0, st>>>(V.n, V.sell->dinv, b, h->omega, V.x);
+        KERNEL_CHECK();
+        NODAL_TRY(sell_sweep<1>(h, V, b, V.x, V.r, nullptr, st));
+        amg_restrict_kernel<<<rows_grid(ctx, V.nc), AT, 0, st>>>(V.nc, V.pt_ptr, V.pt_idx, V.r,
+                                                              h->lv[l + 1].b);
+        KERNEL_CHECK();
+    }
+    {
+        const AmgLevel& V = h->lv[last];
+        const double* b = last == 0 ? b0 : V.b;
+        double* x = last == 0 ? z0 : V.x;
+        if (h->inv) amg_gemv_kernel<<<rows_grid(ctx, (int64_t)V.n * 32), AT, 0, st>>>(V.n, h->inv, b, x);
+        else amg_jacobi0_kernel<<<rows_grid(ctx, V.n), AT, 0, st>>>(V.n, V.sell->dinv, b, h->omega, x);
+        KERNEL_CHECK();
+    }
+    for (int l = last - 1; l >= 0; --l) {
+        const AmgLevel& V = h->lv[l];
+        const double* b = l == 0 ? b0 : V.b;
+        double* xa = V.r;       // the residual is not needed any more
+        amg_prolong_kernel<<<rows_grid(ctx, V.n), AT, 0, st>>>(V.n, V.agg, h->lv[l + 1].x, h->scale,
+                                                             V.x, xa);
+        KERNEL_CHECK();
+        NODAL_TRY(sell_sweep<2>(h, V, b, xa, l == 0 ? z0 : V.x, nullptr, st));
+    }
+    return NODAL_OK;
+}
+
+}  // namespace
+
+extern "C" int nodal_amg_destroy(nodal_amg* h) {
+    if (!h) return NODAL_OK;
+    cudaSetDevice(h->device);
+    nodal_ctx* ctx = h->ctx;
+    for (AmgLevel& V : h->lv) {
+        sell_free(V.sell);
+        if (V.owned) {
+            ctx_pool_free(ctx, const_cast<int32_t*>(V.indptr));
+            ctx_pool_free(ctx, const_cast<int32_t*>(V.indices));
+            ctx_pool_free(ctx, const_cast<double*>(V.data));
+        }
+        ctx_pool_free(ctx, V.agg);
+        ctx_pool_free(ctx, V.pt_ptr);
+        ctx_pool_free(ctx, V.pt_idx);
+        ctx_pool_free(ctx, V.b);
+        ctx_pool_free(ctx, V.x);
+        ctx_pool_free(ctx, V.r);
+    }
+    ctx_pool_free(ctx, h->inv);
+    ctx_pool_free(ctx, h->p);
+    ctx_pool_free(ctx, h->q);
+    ctx_pool_free(ctx, h->r);
+    ctx_pool_free(ctx, h->z);
+    ctx_pool_free(ctx, h->part);
+    delete h;
+    return NODAL_OK;
+}
+
+extern "C" int nodal_amg_create(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
+                                const int32_t* indices, const double* data, const double* params,
+                                nodal_amg** out, void* stream) {
+    if (!ctx || n < 0 || nnz < 0 || !out) return NODAL_BAD_ARG;
+    *out = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    nodal_amg* h = new nodal_amg();
+    h->ctx = ctx;
+    h->device = ctx->device;
+    if (params) {
+        if (params[0] >= 1.0) h->passes = (int)params[0];
+        if (params[1] >= 1.0) h->coarse = (int)params[1];
+        if (params[2] > 0.0) h->omega = params[2];
+        if (params[3] > 0.0) h->scale = params[3];
+        if (params[4] >= 1.0) h->maxlevels = (int)params[4];
+        if (params[5] >= 1.0) h->rounds = (int)params[5];
+        if (params[6] >= 1.0) h->direct_max = (int)params[6];
+    }
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    cudaEventRecord(e0, st);
+    int rc = NODAL_OK;
+    if (n > 0) rc = build_hierarchy(h, n, nnz, indptr, indices, data, st);
+    if (rc == NODAL_OK && n > 0) {
+        h->nparts = std::max(sell_grid(ctx, h->lv[0].sell->nslices), rows_grid(ctx, n));
+        h->p = pool<double>(ctx, n);
+        h->q = pool<double>(ctx, n);
+        h->r = pool<double>(ctx, n);
+        h->z = pool<double>(ctx, n);
+        h->part = pool<double>(ctx, 3 * (size_t)h->nparts + 16);
+        if (!h->p || !h->q || !h->r || !h->z || !h->part) rc = NODAL_CUDA_ERROR;
+    }
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&h->setup_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc != NODAL_OK) {
+        nodal_amg_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return NODAL_OK;
+}
+
+extern "C" int nodal_amg_info(const nodal_amg* h, int32_t cap, int32_t* nlevels, int64_t* rows,
+                              int64_t* nnz, double* setup_ms, int32_t* direct) {
+    if (!h || !nlevels) return NODAL_BAD_ARG;
+    *nlevels = (int32_t)h->lv.size();
+    for (int32_t l = 0; l < *nlevels && l < cap; ++l) {
+        if (rows) rows[l] = h->lv[l].n;
+        if (nnz) nnz[l] = h->lv[l].nnz;
+    }
+    if (setup_ms) *setup_ms = h->setup_ms;
+    if (direct) *direct = h->inv ? 1 : 0;
+    return NODAL_OK;
+}
+
+extern "C" int nodal_amg_fetch_level(nodal_ctx* ctx, const nodal_amg* h, int32_t level, int32_t* agg,
+                                     int32_t* indptr, int32_t* indices, double* data, void* stream) {
+    if (!ctx || !h || level < 0 || level >= (int32_t)h->lv.size()) return NODAL_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const AmgLevel& V = h->lv[level];
+    if (agg) {
+        if (!V.agg) return NODAL_BAD_ARG;   // the coarsest level has no aggregates
+        CUDA_TRY(cudaMemcpyAsync(agg, V.agg, sizeof(int32_t) * (size_t)V.n, cudaMemcpyDeviceToDevice, st));
+    }
+    if (indptr) CUDA_TRY(cudaMemcpyAsync(indptr, V.indptr, sizeof(int32_t) * ((size_t)V.n + 1), cudaMemcpyDeviceToDevice, st));
+    if (indices) CUDA_TRY(cudaMemcpyAsync(indices, V.indices, sizeof(int32_t) * (size_t)V.nnz, cudaMemcpyDeviceToDevice, st));
+    if (data) CUDA_TRY(cudaMemcpyAsync(data, V.data, sizeof(double) * (size_t)V.nnz, cudaMemcpyDeviceToDevice, st));
+    return NODAL_OK;
+}
+
+extern "C" int nodal_amg_apply(nodal_ctx* ctx, const nodal_amg* h, const double* r, double* z,
+                               void* stream) {
+    if (!ctx || !h || h->ctx != ctx) return NODAL_BAD_ARG;
+    if (h->lv.empty()) return NODAL_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return cycle(h, r, z, (cudaStream_t)stream);
+}
+
+extern "C" int nodal_amg_pcg(nodal_ctx* ctx, nodal_amg* h, const double* rhs, double* x, double rtol,
+                             int32_t maxit, int32_t* iters_h, double* relres_h, double* stats_h,
+                             void* stream) {
+    if (!ctx || !h || h->ctx != ctx || !iters_h || !relres_h) return NODAL_BAD_ARG;
+    *iters_h = 0;
+    *relres_h = 0.0;
+    if (stats_h) memset(stats_h, 0, 16 * sizeof(double));
+    if (h->lv.empty()) return NODAL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const AmgLevel& A = h->lv[0];
+    const int32_t n = A.n;
+    const int gv = rows_grid(ctx, n);                        // vector kernels
+    const int gs = sell_grid(ctx, A.sell->nslices);          // SELL sweeps
+    double* part_pq = h->part;
+    double* part_rr = h->part + h->nparts;
+    double* part_rz = h->part + 2 * (size_t)h->nparts;
+    double* scal = h->part + 3 * (size_t)h->nparts;          // [0..1] rz (parity), [2] norm scratch
+    double* host = reinterpret_cast<double*>(ctx->pinned);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int iters = 0, restarts = 0, rc = NODAL_NOT_CONVERGED;
+    double relres = 0.0;
+    bool timed = false;
+
+    // ||v||^2 of a device vector pair -> host
+    auto dot_to_host = [&](const double* a, const double* b, double* result) -> int {
+        apcg_dot_kernel<<<gv, AT, 0, st>>>(n, a, b, part_rr);
+        KERNEL_CHECK();
+        apcg_sum_kernel<<<1, AT, 0, st>>>(part_rr, gv, scal + 2);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(host, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *result = host[0];
+        return NODAL_OK;
+    };
+    auto run = [&]() -> int {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        double bb = 0.0, rr = 0.0;
+        NODAL_TRY(dot_to_host(rhs, rhs, &bb));
+        if (!(bb > 0.0)) {                                   // b = 0 -> x = 0
+            if (bb == 0.0) {
+                CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
+                rc = NODAL_OK;
+                return NODAL_OK;
+            }
+            nodal_set_error("nodal_amg_pcg: the right-hand side is not finite");
+            rc = NODAL_BREAKDOWN;
+            return NODAL_OK;
+        }
+        const double bnorm = sqrt(bb);
+        NODAL_TRY(sell_sweep<1>(h, A, rhs, x, h->r, nullptr, st));       // r = b - A x0
+        NODAL_TRY(dot_to_host(h->r, h->r, &rr));
+        relres = sqrt(rr) / bnorm;
+        while (true) {
+            if (relres <= rtol) { rc = NODAL_OK; break; }
+            if (iters >= maxit) { rc = NODAL_NOT_CONVERGED; break; }
+            if (restarts > 8) { rc = NODAL_NOT_CONVERGED; break; }
+            // (re)start from the current r
+            int par = 0;
+            NODAL_TRY(cycle(h, h->r, h->z, st));
+            apcg_dot_kernel<<<gv, AT, 0, st>>>(n, h->r, h->z, part_rz);
+            KERNEL_CHECK();
+            apcg_direction_kernel<<<gv, AT, 0, st>>>(n, part_rz, gv, scal + (par ^ 1), scal + par, h->z, h->p, 1);
+            KERNEL_CHECK();
+            bool broke = false;
+            while (iters < maxit) {
+                NODAL_TRY(sell_sweep<0>(h, A, nullptr, h->p, h->q, part_pq, st));
+                apcg_update_kernel<<<gv, AT, 0, st>>>(n, part_pq, gs, scal + par, h->p, h->q, x, h->r, part_rr);
+                KERNEL_CHECK();
+                apcg_sum_kernel<<<1, AT, 0, st>>>(part_rr, gv, scal + 2);
+                KERNEL_CHECK();
+                CUDA_TRY(cudaMemcpyAsync(host, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                ++iters;
+                rr = host[0];
+                if (!std::isfinite(rr)) { broke = true; break; }
+                if (sqrt(rr) <= rtol * bnorm) break;
+                NODAL_TRY(cycle(h, h->r, h->z, st));
+                apcg_dot_kernel<<<gv, AT, 0, st>>>(n, h->r, h->z, part_rz);
+                KERNEL_CHECK();
+                apcg_direction_kernel<<<gv, AT, 0, st>>>(n, part_rz, gv, scal + par, scal + (par ^ 1), h->z, h->p, 0);
+                KERNEL_CHECK();
+                par ^= 1;
+            }
+            if (broke) {
+                nodal_set_error("nodal_amg_pcg: breakdown (non-finite residual) at iteration %d", iters);
+                rc = NODAL_BREAKDOWN;
+                break;
+            }
+            // the recurrence says converged (or maxit): check the true residual
+            NODAL_TRY(sell_sweep<1>(h, A, rhs, x, h->r, nullptr, st));
+            NODAL_TRY(dot_to_host(h->r, h->r, &rr));
+            relres = sqrt(rr) / bnorm;
+            if (!std::isfinite(relres)) { rc = NODAL_BREAKDOWN; break; }
+            if (relres > rtol) ++restarts;
+        }
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        timed = true;
+        return NODAL_OK;
+    };
+    const int st_run = run();
+    float ms = 0.f;
+    if (st_run == NODAL_OK && timed) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (st_run != NODAL_OK) return st_run;
+    *iters_h = iters;
+    *relres_h = relres;
+    if (stats_h) {
+        double rows = 0.0, nnz = 0.0;
+        for (const AmgLevel& V : h->lv) { rows += V.n; nnz += (double)V.nnz; }
+        stats_h[0] = (double)h->lv.size();
+        stats_h[1] = A.nnz ? nnz / (double)A.nnz : 0.0;       // operator complexity
+        stats_h[2] = restarts;
+        stats_h[3] = ms;
+        stats_h[4] = h->setup_ms;
+        stats_h[5] = h->lv.back().n;
+        stats_h[6] = n ? rows / n : 0.0;                       // grid complexity
+        stats_h[7] = h->inv ? 1.0 : 0.0;
+    }
+    return rc;
+}

@@ -62,6 +62,88 @@ class DeviceCSR:
         return a if dtype is None else a.astype(dtype)
 
 
+class DeviceAMG:
+    """Handle of a nodal_amg hierarchy; keeps the matrix arrays alive while it exists."""
+
+    PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max")
+
+    def __init__(self, dev, csr, **params):
+        unknown = set(params) - set(self.PARAMS)
+        if unknown:
+            raise TypeError(f"unknown AMG parameter(s): {sorted(unknown)}")
+        self.dev, self.csr = dev, csr
+        arr = (C.c_double * 8)(*[float(params.get(k, 0.0)) for k in self.PARAMS], 0.0)
+        h = C.c_void_p()
+        p = dev.ptr
+        st = dev.lib.nodal_amg_create(dev.ctx, csr.n, csr.nnz, p(csr.indptr), p(csr.indices), p(csr.data),
+                                      arr, C.byref(h), dev.stream())
+        _lib.check(st, "nodal_amg_create")
+        self.handle = h
+        cap = 64
+        nl, rows, nnz = C.c_int32(0), (C.c_int64 * cap)(), (C.c_int64 * cap)()
+        ms, direct = C.c_double(0.0), C.c_int32(0)
+        _lib.check(dev.lib.nodal_amg_info(h, cap, C.byref(nl), rows, nnz, C.byref(ms), C.byref(direct)),
+                   "nodal_amg_info")
+        self.rows = [int(rows[k]) for k in range(nl.value)]
+        self.nnz = [int(nnz[k]) for k in range(nl.value)]
+        self.setup_ms, self.direct = ms.value, bool(direct.value)
+
+    def close(self):
+        if self.handle:
+            self.dev.lib.nodal_amg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
+
+    def aggregates(self, level):
+        """Row -> aggregate map of `level` (device int32 tensor)."""
+        dev = self.dev
+        agg = dev.empty(max(1, self.rows[level]), dev.torch.int32)[: self.rows[level]]
+        _lib.check(dev.lib.nodal_amg_fetch_level(dev.ctx, self.handle, level, dev.ptr(agg), None, None, None,
+                                                 dev.stream()), "nodal_amg_fetch_level")
+        return agg
+
+    def operator(self, level):
+        """The level's operator as a DeviceCSR copy."""
+        dev, torch = self.dev, self.dev.torch
+        n, nnz = self.rows[level], self.nnz[level]
+        indptr = dev.empty(n + 1, torch.int32)
+        indices = dev.empty(max(1, nnz), torch.int32)[:nnz]
+        data = dev.empty(max(1, nnz), torch.float64)[:nnz]
+        p = dev.ptr
+        _lib.check(dev.lib.nodal_amg_fetch_level(dev.ctx, self.handle, level, None, p(indptr), p(indices),
+                                                 p(data), dev.stream()), "nodal_amg_fetch_level")
+        return DeviceCSR(n, indptr, indices, data)
+
+    def apply(self, r):
+        """z = M r: one V-cycle."""
+        dev = self.dev
+        z = dev.empty(max(1, self.csr.n), dev.torch.float64)[: self.csr.n]
+        _lib.check(dev.lib.nodal_amg_apply(dev.ctx, self.handle, dev.ptr(r), dev.ptr(z), dev.stream()),
+                   "nodal_amg_apply")
+        return z
+
+    def solve(self, rhs, rtol=1e-10, maxit=None, x0=None):
+        dev, n = self.dev, self.csr.n
+        x = dev.zeros(max(2, n), dev.torch.float64)[:n] if x0 is None else x0.clone()
+        if maxit is None:
+            maxit = 1000
+        iters, relres = C.c_int32(0), C.c_double(0.0)
+        stats = (C.c_double * 16)()
+        st = dev.lib.nodal_amg_pcg(dev.ctx, self.handle, dev.ptr(rhs), dev.ptr(x), rtol, maxit,
+                                   C.byref(iters), C.byref(relres), stats, dev.stream())
+        _lib.check(st, "nodal_amg_pcg", allowed=(_lib.OK, _lib.NOT_CONVERGED, _lib.BREAKDOWN))
+        info = dict(solver="amg_pcg", status=st, iterations=iters.value, relres=relres.value,
+                    restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4], levels=int(stats[0]),
+                    operator_complexity=stats[1], grid_complexity=stats[6], coarsest_rows=int(stats[5]),
+                    coarsest_direct=bool(stats[7]), level_rows=list(self.rows))
+        return x, info
+
+
 class Device:
     """One CUDA device + one library context.  Not thread safe (one per thread)."""
 
@@ -210,6 +292,18 @@ class Device:
             info["kernel_ms"] = dict(spmv_dot=stats[8], update=stats[9], direction=stats[10],
                                      samples=int(stats[11]))
         return x, info
+
+    def amg(self, csr: DeviceCSR, **params):
+        """Aggregation-AMG hierarchy for an SPD DeviceCSR (csrc/amg.cu); see DeviceAMG."""
+        return DeviceAMG(self, csr, **params)
+
+    def amg_pcg(self, csr: DeviceCSR, rhs, rtol=1e-10, maxit=None, x0=None, **params):
+        """AMG-preconditioned CG, hierarchy built and dropped inside the call."""
+        amg = DeviceAMG(self, csr, **params)
+        try:
+            return amg.solve(rhs, rtol=rtol, maxit=maxit, x0=x0)
+        finally:
+            amg.close()
 
     def gmres(self, csr: DeviceCSR, rhs, rtol=1e-12, restart=60, maxit=20000):
         n = csr.n

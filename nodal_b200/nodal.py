@@ -300,7 +300,13 @@ class Circuit:
         dev = self._dev
         if self.sparse:
             rtol = self.options.get("rtol", 1e-10)
-            if self.table.is_spd_structured():
+            precond = self.options.get("precond", "jacobi")
+            if precond not in ("jacobi", "amg"):
+                raise ValueError(f"precond must be 'jacobi' or 'amg', got {precond!r}")
+            if self.table.is_spd_structured() and precond == "amg":
+                x, info = dev.amg_pcg(self.G, self.A, rtol=rtol, maxit=self.options.get("maxit"),
+                                      **self.options.get("amg", {}))
+            elif self.table.is_spd_structured():
                 x, info = dev.pcg(self.G, self.A, rtol=rtol, maxit=self.options.get("maxit"),
                                   flags=self.options.get("pcg_flags", 0))
             else:

@@ -54,6 +54,46 @@ def stamp_host_lib():
     return _stamp_host
 
 
+_amg_host = None
+
+
+def amg_host_lib():
+    """CPU compilation of csrc/amg_core.cuh (aggregation rules) for the not-gpu tests."""
+    global _amg_host
+    if _amg_host is None:
+        out = os.path.join(HERE, "host_check", "_build")
+        os.makedirs(out, exist_ok=True)
+        so = os.path.join(out, "libamg_host.so")
+        src = os.path.join(HERE, "host_check", "amg_host.cpp")
+        core = os.path.join(ROOT, "nodal_b200", "csrc", "amg_core.cuh")
+        if (not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src),
+                                                                  os.path.getmtime(core))):
+            subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+        lib = C.CDLL(so)
+        lib.amg_edge_hash_host.restype = C.c_uint32
+        lib.amg_edge_hash_host.argtypes = [C.c_int32, C.c_int32]
+        lib.amg_aggregate_host.restype = C.c_int32
+        lib.amg_aggregate_host.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_void_p]
+        _amg_host = lib
+    return _amg_host
+
+
+def amg_aggregate_on_host(A, rounds=8):
+    """(match, agg, nc) of one pairwise pass over scipy CSR `A`, computed by the shared device core."""
+    A = A.tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    indptr = np.ascontiguousarray(A.indptr, np.int32)
+    indices = np.ascontiguousarray(A.indices, np.int32)
+    data = np.ascontiguousarray(A.data, np.float64)
+    match = np.empty(n, np.int32)
+    agg = np.empty(n, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    nc = amg_host_lib().amg_aggregate_host(n, p(indptr), p(indices), p(data), rounds, p(match), p(agg))
+    return match, agg, nc
+
+
 def stamp_on_host(table, stride):
     """(rows, cols, vals) the stamp kernel would emit, computed by the shared core on the CPU."""
     lib = stamp_host_lib()

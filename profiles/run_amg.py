@@ -3,8 +3,11 @@
 Prints one JSON line per grid side: hierarchy, setup / solve time, iterations, R."""
 import copy
 import json
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 

@@ -68,8 +68,12 @@ def test_cycle_equals_numpy_statement(device, name):
 @pytest.mark.parametrize("name", ["grid40", "grid96", "grid200", "random", "random_mid"])
 def test_amg_pcg_solves_like_scipy(device, name):
     A, b = cases(name)
-    x_ref = spla.spsolve(sps.csc_matrix(A), b)
-    _, it_ref = mirror.pcg(A, b, mirror.AMG(A))
+    M = mirror.AMG(A)
+    _, it_ref = mirror.pcg(A, b, M)
+    if name.startswith("grid"):
+        x_ref = spla.spsolve(sps.csc_matrix(A), b)
+    else:               # SuperLU fills in catastrophically on the random graphs: tight CG on the CPU instead
+        x_ref, _ = mirror.pcg(A, b, M, rtol=1e-13)
     x, info = device.amg_pcg(to_device_csr(device, A), device.to_device(b), rtol=1e-10)
     x = x.cpu().numpy()
     assert info["status"] == 0

@@ -24,8 +24,7 @@ def _torch():
 
 def coo_stride(table: ComponentTable) -> int:
     """Slots per component the stamp kernel must reserve (see include/nodal_b200.h)."""
-    present = np.unique(table.type)
-    need = max((_STRIDE_OF_TYPE[int(t)] for t in present), default=2)
+    need = max((_STRIDE_OF_TYPE[t] for t in table.present_types()), default=2)
     return 2 if need <= 2 else 4 if need <= 4 else need
 
 

@@ -27,7 +27,7 @@ MAX_TRIPLES = 6
 
 
 class ComponentTable:
-    __slots__ = tuple(n for n, _ in _COLS) + ("kcl", "be", "_pinned")
+    __slots__ = tuple(n for n, _ in _COLS) + ("kcl", "be", "_pinned", "_facts")
 
     def __init__(self, type, value, a, b, c=None, d=None, drv=None, branch=None, kcl=0, be=0):
         n = len(type)
@@ -44,6 +44,7 @@ class ComponentTable:
         self.kcl = int(kcl)
         self.be = int(be)
         self._pinned = None
+        self._facts = None
         for name, _ in _COLS:
             if len(getattr(self, name)) != n:
                 raise ValueError(f"column {name} has wrong length")
@@ -84,26 +85,67 @@ class ComponentTable:
         self._pinned = pinned
         return self
 
+    # ---- cached column scans -------------------------------------------------------
+    # Every question the host asks about the columns (which types occur, are all resistances
+    # positive, are the indices in range) is answered by one scan that is kept with the table:
+    # at 33.5 M components the separate numpy passes (np.unique, boolean masks, fancy indexing)
+    # cost 0.7 s per Circuit, several times the GPU time of the whole solve.  The columns are
+    # treated as frozen once scanned; call ``invalidate()`` after editing them in place.
+    def invalidate(self):
+        self._facts = None
+
+    def facts(self):
+        f = self._facts
+        if f is not None:
+            return f
+        t, m = self.type, len(self)
+        f = dict(present=0, unknown_type=False, r_zero=False, r_nonpositive=False)
+        if m:
+            f["unknown_type"] = bool(t.max() >= len(K.TYPE_NAME))
+            if not f["unknown_type"]:
+                f["present"] = int(np.bitwise_or.reduce(np.left_shift(np.uint8(1), t, dtype=np.uint8)))
+            else:
+                f["present"] = sum(1 << int(k) for k in np.unique(t) if k < 8)
+            has = lambda code: bool(f["present"] >> code & 1)          # noqa: E731
+            if has(K.T_R):
+                positive = self.value > 0            # False for 0, negatives and NaN
+                if f["present"] != 1 << K.T_R:
+                    positive |= t != K.T_R
+                if not bool(positive.all()):
+                    f["r_nonpositive"] = True
+                    zero = self.value == 0
+                    zero &= t == K.T_R
+                    f["r_zero"] = bool(zero.any())
+        self._facts = f
+        return f
+
+    def has_type(self, code):
+        return bool(self.facts()["present"] >> code & 1)
+
+    def present_types(self):
+        return [k for k in range(len(K.TYPE_NAME)) if self.has_type(k)]
+
     def is_resistive(self):
-        return bool(np.all(self.type == K.T_R))
+        return len(self) == 0 or self.facts()["present"] == 1 << K.T_R
 
     def is_spd_structured(self):
         """Only R (positive) and A rows: G is a weighted graph Laplacian with the
         ground row removed -> symmetric positive definite if connected."""
-        t = self.type
-        ok = (t == K.T_R) | (t == K.T_A)
-        if not bool(np.all(ok)):
+        f = self.facts()
+        if f["unknown_type"] or f["present"] & ~((1 << K.T_R) | (1 << K.T_A)):
             return False
-        r = t == K.T_R
-        return bool(np.all(self.value[r] > 0))
+        return not f["r_nonpositive"]
 
     def validate(self):
         """Host-side checks the reference performs while stamping."""
-        t = self.type
-        if np.any((t == K.T_R) & (self.value == 0)):
+        f = self.facts()
+        if f.get("validated"):
+            return
+        if f["r_zero"]:
             raise ValueError("Model error: resistors can't have null resistance")
-        cc = (t == K.T_CCVS) | (t == K.T_CCCS)
-        if np.any(cc):
+        if self.has_type(K.T_CCVS) or self.has_type(K.T_CCCS):
+            t = self.type
+            cc = (t == K.T_CCVS) | (t == K.T_CCCS)
             drv = self.drv[cc]
             if np.any(drv < 0):
                 raise KeyError("Driving component not found")
@@ -112,13 +154,15 @@ class ComponentTable:
                 raise AttributeError("only resistors are supported as driving components")
             if np.any(self.value[drv] == 0):
                 raise ZeroDivisionError("float division by zero")
-        lim = self.kcl
-        for name in ("a", "b"):
-            v = getattr(self, name)
-            if np.any(v >= lim) or np.any(v < K.GROUND):
-                raise ValueError(f"lead index out of range in column {name}")
-        if np.any(self.branch >= self.be):
-            raise ValueError("branch index out of range")
+        if len(self):
+            lim = self.kcl
+            for name in ("a", "b"):
+                v = getattr(self, name)
+                if v.max() >= lim or v.min() < K.GROUND:
+                    raise ValueError(f"lead index out of range in column {name}")
+            if self.branch.max() >= self.be:
+                raise ValueError("branch index out of range")
+        f["validated"] = True
 
     def coo_upper_bound(self):
         return MAX_TRIPLES * len(self)

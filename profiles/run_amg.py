@@ -1,6 +1,7 @@
 """Timing of the opt-in AMG-PCG path on 2-D grids (run on the GPU box):
     python profiles/run_amg.py 1024 2048 4096
-Prints one JSON line per grid side: hierarchy, setup / solve time, iterations, R."""
+Prints one JSON line per grid side: hierarchy, setup / solve time, iterations, R.
+NODAL_AMG_REPS=1 runs a single (cold) pass, for launch lists under ncu."""
 import copy
 import json
 import os
@@ -22,7 +23,7 @@ for N in [int(a) for a in sys.argv[1:]] or [1024]:
     dtab = dev.upload_table(table)
     row = net.nodenum["1"]
     out = {"grid": N, "unknowns": table.n}
-    for rep in range(2):                                  # first pass warms allocations up
+    for rep in range(int(os.environ.get("NODAL_AMG_REPS", "2"))):   # first pass warms allocations up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         csr, rhs = dev.assemble_csr(table, dtab=dtab)

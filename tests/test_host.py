@@ -240,3 +240,46 @@ def test_cli_error_paths_without_gpu(tmp_path, capsys):
     assert "not found in netlist" in capsys.readouterr().out
     assert solver.parser.parse_args(["x.csv", "-s"]).sparse is True
     assert equiv.parser.parse_args(["x.csv"]).sparse is False
+
+
+def test_table_column_scan_is_cached_and_equals_direct_checks():
+    """ComponentTable.facts(): one cached scan answers validate / is_spd_structured / stride."""
+    from nodal_b200 import constants as K
+    from nodal_b200.device import coo_stride
+    from nodal_b200.table import ComponentTable
+    rng = np.random.default_rng(0)
+    m = 1000
+    a = rng.integers(-1, 50, m).astype(np.int32)
+    b = rng.integers(-1, 50, m).astype(np.int32)
+    t = ComponentTable(np.zeros(m, np.uint8), rng.uniform(1, 2, m), a, b, kcl=50, be=0)
+    assert t.is_resistive() and t.is_spd_structured() and t.present_types() == [K.T_R]
+    assert coo_stride(t) == 4
+    t.validate()
+    assert t.facts()["validated"]
+    t.value[17] = 0.0                      # edited in place: stale until invalidate()
+    t.invalidate()
+    assert not t.is_spd_structured()
+    with pytest.raises(ValueError, match="null resistance"):
+        t.validate()
+    t.value[17] = -3.0
+    t.invalidate()
+    t.validate()                           # the reference stamps negative resistances happily
+    assert not t.is_spd_structured()
+    t.value[17] = np.nan
+    t.invalidate()
+    assert not t.is_spd_structured()
+    mixed = t.copy()                       # a copy starts without cached facts
+    mixed.value[17] = 1.0
+    mixed.type[3] = K.T_A
+    assert mixed.is_spd_structured() and not mixed.is_resistive()
+    assert mixed.present_types() == [K.T_R, K.T_A] and coo_stride(mixed) == 4
+    mixed.type[4] = K.T_E
+    mixed.invalidate()
+    assert not mixed.is_spd_structured() and coo_stride(mixed) == 5
+    bad = t.copy()
+    bad.a[5] = 50
+    with pytest.raises(ValueError, match="out of range"):
+        bad.validate()
+    empty = ComponentTable(np.zeros(0, np.uint8), np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
+    empty.validate()
+    assert empty.is_resistive() and empty.present_types() == [] and coo_stride(empty) == 2

@@ -174,6 +174,17 @@ int nodal_amg_apply(nodal_ctx* ctx, const nodal_amg* amg, const double* r, doubl
 int nodal_amg_pcg(nodal_ctx* ctx, nodal_amg* amg, const double* rhs, double* x, double rtol,
                   int32_t maxit, int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
 
+/* ---------------------------------------------------------------- connectivity
+ * Connected components of the lead graph (nodes 0..kcl-1 plus ground = node kcl; one edge
+ * anode - bnode per component, ground leads are negative indices).  Replaces the breadth-first
+ * search is_connected (nodal/nodal.py:88-105) behind the singular-matrix diagnosis
+ * (nodal/nodal.py:328-335).  labels (device, kcl + 1 entries, or NULL) receives the smallest
+ * node index of every node's component; *ncomponents_h the number of components,
+ * *reached_h the number of nodes connected to ground (== kcl + 1 iff the circuit is connected). */
+int nodal_connected_components(nodal_ctx* ctx, int64_t ncomp, const int32_t* a, const int32_t* b,
+                               int32_t kcl, int32_t* labels, int32_t* ncomponents_h,
+                               int32_t* reached_h, void* stream);
+
 /* ---------------------------------------------------------------- dense kernels
  * Blocked FP64 LU with partial pivoting + triangular solves.  Replaces
  * numpy.linalg.solve (LAPACK dgesv) at nodal/nodal.py:327.  G (n x n row-major)

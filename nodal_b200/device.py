@@ -292,6 +292,18 @@ class Device:
                                      samples=int(stats[11]))
         return x, info
 
+    def connected_components(self, table: ComponentTable, want_labels=False):
+        """(number of components, nodes connected to ground, labels or None) of the lead graph:
+        nodes 0..kcl-1 plus ground (= node kcl), one edge per component (csrc/graph.cu)."""
+        a, b = self.to_device(table.a), self.to_device(table.b)
+        labels = self.empty(table.kcl + 1, self.torch.int32) if want_labels else None
+        count, reached = C.c_int32(0), C.c_int32(0)
+        st = self.lib.nodal_connected_components(self.ctx, len(table), self.ptr(a), self.ptr(b), table.kcl,
+                                                 self.ptr(labels) if want_labels else None,
+                                                 C.byref(count), C.byref(reached), self.stream())
+        _lib.check(st, "nodal_connected_components")
+        return count.value, reached.value, labels
+
     def amg(self, csr: DeviceCSR, **params):
         """Aggregation-AMG hierarchy for an SPD DeviceCSR (csrc/amg.cu); see DeviceAMG."""
         return DeviceAMG(self, csr, **params)

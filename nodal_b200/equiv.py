@@ -47,6 +47,23 @@ def equivalent_resistance(netlist, a, b, sparse=False, **options):
     return potential(a) - potential(b)
 
 
+def equivalent_resistances(netlist, pairs, sparse=True, **options):
+    """Many-port form: [R(a, b) for (a, b) in pairs] with the matrix assembled once and, with
+    precond="amg", one AMG hierarchy shared by all right-hand sides.
+    Each value equals equivalent_resistance(netlist, a, b) to the solver tolerance; same errors."""
+    if not check_resistive(netlist):
+        raise ValueError("Network is not resistive")
+    pairs = [tuple(p) for p in pairs]
+    for pair in pairs:
+        for node in pair:
+            if node != netlist.ground and node not in netlist.nodenum:
+                raise KeyError(f"Node `{node}` not found in netlist")
+    circuit = n.Circuit(netlist, sparse=sparse, **options)
+    values = circuit.port_resistances(pairs)
+    equivalent_resistances.last_stats = circuit.stats
+    return values
+
+
 def main(argv=None):
     options = parser.parse_args(argv)
     netlist = load_netlist_or_exit(options.netlist_path)

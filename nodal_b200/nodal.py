@@ -294,25 +294,52 @@ class Circuit:
         return self.G.cpu().numpy()
 
     # ---- solve ------------------------------------------------------------------
+    def _sparse_solver(self):
+        """Which device solver the sparse path uses: "amg", "pcg" or "gmres"."""
+        precond = self.options.get("precond", "jacobi")
+        if precond not in ("jacobi", "amg"):
+            raise ValueError(f"precond must be 'jacobi' or 'amg', got {precond!r}")
+        if not self.table.is_spd_structured():
+            return "gmres"
+        return "amg" if precond == "amg" else "pcg"
+
+    def _device_solve(self, rhs, amg=None):
+        """x, info for G x = rhs on the device (rhs is a device tensor; dense G is not modified)."""
+        dev = self._dev
+        if not self.sparse:
+            return dev.lu_solve(self.G.clone(), rhs)
+        kind = self._sparse_solver()
+        rtol = self.options.get("rtol", 1e-10)
+        if kind == "amg" and amg is not None:
+            return amg.solve(rhs, rtol=rtol, maxit=self.options.get("maxit"))
+        if kind == "amg":
+            return dev.amg_pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                               **self.options.get("amg", {}))
+        if kind == "pcg":
+            return dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                           flags=self.options.get("pcg_flags", 0))
+        return dev.gmres(self.G, rhs, rtol=self.options.get("rtol", 1e-12),
+                         restart=self.options.get("restart", 60),
+                         maxit=self.options.get("maxit") or 20000)
+
+    def is_connected(self):
+        """Every node reaches ground through component leads (the reference's is_connected,
+        nodal.py:88-105), decided on the device from the component table."""
+        _, reached, _ = self._dev.connected_components(self.table)
+        return reached == self.table.kcl + 1
+
     def solve(self):
         """Raises numpy.linalg.LinAlgError (singular dense system) or
-        UnconnectedCircuitError (floating nodes), as the reference does."""
-        dev = self._dev
+        UnconnectedCircuitError (floating nodes), as the reference does.  The sparse path
+        mirrors scipy (no exception; a Krylov solver even returns a finite solution when the
+        singular system is consistent) unless the Circuit was built with check_connected=True:
+        then the lead graph is checked on the device first and an unconnected circuit raises
+        UnconnectedCircuitError like the dense path."""
+        if self.sparse and self.options.get("check_connected") and not self.is_connected():
+            logging.error("Model error: unconnected circuit")
+            raise UnconnectedCircuitError
+        x, info = self._device_solve(self.A)
         if self.sparse:
-            rtol = self.options.get("rtol", 1e-10)
-            precond = self.options.get("precond", "jacobi")
-            if precond not in ("jacobi", "amg"):
-                raise ValueError(f"precond must be 'jacobi' or 'amg', got {precond!r}")
-            if self.table.is_spd_structured() and precond == "amg":
-                x, info = dev.amg_pcg(self.G, self.A, rtol=rtol, maxit=self.options.get("maxit"),
-                                      **self.options.get("amg", {}))
-            elif self.table.is_spd_structured():
-                x, info = dev.pcg(self.G, self.A, rtol=rtol, maxit=self.options.get("maxit"),
-                                  flags=self.options.get("pcg_flags", 0))
-            else:
-                x, info = dev.gmres(self.G, self.A, rtol=self.options.get("rtol", 1e-12),
-                                    restart=self.options.get("restart", 60),
-                                    maxit=self.options.get("maxit") or 20000)
             e = x.cpu().numpy()
             if info["status"] != 0:
                 # the reference's sparse path does not raise on singular systems: scipy warns
@@ -321,10 +348,8 @@ class Circuit:
                 if info["status"] == 3 or not np.all(np.isfinite(e)):
                     e = np.full_like(e, np.nan)
         else:
-            work = self.G.clone()
-            x, info = dev.lu_solve(work, self.A)
             if info["status"] == 1:
-                if not is_connected(self.netlist):
+                if not self.is_connected():
                     logging.error("Model error: unconnected circuit")
                     raise UnconnectedCircuitError
                 logging.error("Model error: matrix is singular")
@@ -334,6 +359,49 @@ class Circuit:
         sol = Solution(e, self.netlist, self.currents)
         sol.stats = info
         return sol
+
+    def port_resistances(self, pairs):
+        """e(a) - e(b) for a 1 A source from b to a, for every (a, b) in `pairs`, against the
+        matrix assembled once (many-port equivalent resistance).
+        Only the two potentials of a pair leave the device.  The AMG hierarchy (precond="amg")
+        is built once and shared by all right-hand sides."""
+        dev, torch = self._dev, self._dev.torch
+        n = self.table.n
+        net = self.netlist
+
+        def row(node):
+            return c.GROUND if node == net.ground else net.nodenum[node]
+
+        amg = None
+        if self.sparse and self._sparse_solver() == "amg":
+            amg = dev.amg(self.G, **self.options.get("amg", {}))
+        values, stats = [], []
+        try:
+            for a, b in pairs:
+                ia, ib = row(a), row(b)
+                if ia == ib:
+                    values.append(0.0)
+                    stats.append(dict(solver="none", status=0, iterations=0))
+                    continue
+                rhs = dev.zeros(max(2, n), torch.float64)[:n]
+                if ia != c.GROUND:
+                    rhs[ia] = 1.0
+                if ib != c.GROUND:
+                    rhs[ib] = -1.0
+                x, info = self._device_solve(rhs, amg=amg)
+                if not self.sparse and info["status"] == 1:
+                    raise np.linalg.LinAlgError("Singular matrix")
+                if self.sparse and info["status"] != 0:
+                    warnings.warn(f"sparse solve did not converge ({info})", RuntimeWarning)
+                ea = float(x[ia]) if ia != c.GROUND else 0.0
+                eb = float(x[ib]) if ib != c.GROUND else 0.0
+                values.append(ea - eb)
+                stats.append(info)
+        finally:
+            if amg is not None:
+                amg.close()
+        self.stats = stats
+        return values
 
 
 class Solution:
@@ -348,6 +416,26 @@ class Solution:
         self.ground = netlist.ground
         self.anomnum = netlist.anomnum
         self.stats = {}
+
+    # ---- bulk access: arrays instead of a line per node -----------
+    def potentials(self):
+        """Node potentials in row order (`nodenum[name]` indexes it); ground is 0 V."""
+        return self.result[: self.nums["kcl"]]
+
+    def branch_currents(self):
+        """Currents of the anomalous branches in `anomnum` order."""
+        return self.result[self.nums["kcl"]:]
+
+    def save(self, path, names=False):
+        """Binary export (numpy .npz): result, kcl, ground and, with names=True, the node and
+        branch labels in row order.  Printing a 16 M-node solution sorts and formats every name."""
+        payload = dict(result=np.asarray(self.result), kcl=np.int64(self.nums["kcl"]),
+                       ground=np.array(str(self.ground)))
+        if names:
+            order = sorted(self.nodenum, key=self.nodenum.get)
+            payload["nodes"] = np.array(order, dtype=str)
+            payload["branches"] = np.array(sorted(self.anomnum, key=self.anomnum.get), dtype=str)
+        np.savez(path, **payload)
 
     def __str__(self):
         lines = [f"Ground node: {self.ground}"]

@@ -142,3 +142,32 @@ def test_million_unknown_grid(device):
     assert st["status"] == 0 and st["iterations"] <= 60 and st["relres"] <= 1e-10
     rj = n.equiv.equivalent_resistance(net, "1", "g", sparse=True)
     assert r == pytest.approx(rj, rel=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["dense", "jacobi", "amg"])
+def test_many_port_equivalent_resistances(device, mode):
+    """one assembly (and one AMG hierarchy), many (a, b) pairs; every value
+    equals the single-pair call of the reference API and the oracle."""
+    from oracle import mna_oracle as orc
+    N = 30
+    net = gen.grid2d(N)
+    pairs = [("1", "g"), ("g", "1"), ("n0_0", "n29_29"), ("n3_4", "1"), ("n7_7", "n7_7"), ("n10_2", "g")]
+    kw = dict(sparse=False) if mode == "dense" else dict(sparse=True, precond=mode, rtol=1e-12)
+    if mode == "amg":
+        kw["amg"] = dict(coarse=64)                     # 899 unknowns: force a real hierarchy
+    got = n.equiv.equivalent_resistances(net, pairs, **kw)
+    stats = n.equiv.equivalent_resistances.last_stats
+    assert len(got) == len(stats) == len(pairs)
+    rows = orc.grid2d_rows(N)
+    for (a, b), r, st in zip(pairs, got, stats):
+        if a == b:
+            assert r == 0.0
+            continue
+        want = orc.equivalent_resistance(rows, a, b, sparse=True)
+        assert r == pytest.approx(want, rel=1e-9)
+        assert r == pytest.approx(n.equiv.equivalent_resistance(net, a, b, **kw), rel=1e-9)
+        if mode == "amg":
+            assert st["solver"] == "amg_pcg" and st["levels"] >= 2
+    assert got[0] == pytest.approx(got[1], rel=1e-12)    # symmetric in (a, b)
+    with pytest.raises(KeyError):
+        n.equiv.equivalent_resistances(net, [("1", "nowhere")], **kw)

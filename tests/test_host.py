@@ -283,3 +283,25 @@ def test_table_column_scan_is_cached_and_equals_direct_checks():
     empty = ComponentTable(np.zeros(0, np.uint8), np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
     empty.validate()
     assert empty.is_resistive() and empty.present_types() == [] and coo_stride(empty) == 2
+
+
+def test_solution_bulk_access_and_binary_export(tmp_path):
+    """Solution.potentials / branch_currents / save: arrays instead of one printed line per node."""
+    class FakeNetlist:
+        nodenum = {"b": 1, "a": 0, "zz": 2}
+        nums = {"kcl": 3, "be": 2}
+        ground = "g"
+        anomnum = {"e2": 1, "e1": 0}
+    result = np.array([1.5, -2.0, 0.25, 3.0, -4.0])
+    sol = n.Solution(result, FakeNetlist, ["e1", "e2"])
+    assert np.array_equal(sol.potentials(), result[:3])
+    assert np.array_equal(sol.branch_currents(), result[3:])
+    sol.save(tmp_path / "plain.npz")
+    with np.load(tmp_path / "plain.npz") as z:
+        assert np.array_equal(z["result"], result) and int(z["kcl"]) == 3 and str(z["ground"]) == "g"
+        assert "nodes" not in z
+    sol.save(tmp_path / "named.npz", names=True)
+    with np.load(tmp_path / "named.npz") as z:
+        assert list(z["nodes"]) == ["a", "b", "zz"] and list(z["branches"]) == ["e1", "e2"]
+    text = str(sol)                       # the reference layout is untouched
+    assert text.splitlines()[0] == "Ground node: g" and "e(zz) \t= 0.25" in text and "i(e2) \t= -4.0" in text

@@ -306,9 +306,20 @@ T* pool(nodal_ctx* ctx, size_t count) {
     if (!p) nodal_set_error("amg: out of device memory (%zu bytes)", sizeof(T) * count);
     return p;
 }
-#define POOL(var, type, count)                       \
-    type* var = pool<type>(ctx, (size_t)(count));    \
-    if (!var) return NODAL_CUDA_ERROR
+
+// A pool allocation that goes back to the pool when the scope ends, unless keep() hands it on.
+// (Frees are stream ordered: every user of these buffers runs on the one setup stream.)
+template <typename T>
+struct Scratch {
+    nodal_ctx* ctx;
+    T* ptr;
+    Scratch(nodal_ctx* c, size_t count) : ctx(c), ptr(pool<T>(c, count)) {}
+    ~Scratch() { ctx_pool_free(ctx, ptr); }
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    T* keep() { T* p = ptr; ptr = nullptr; return p; }
+    operator T*() const { return ptr; }
+};
 
 struct Csr {
     int32_t n = 0;
@@ -327,13 +338,13 @@ void free_csr(nodal_ctx* ctx, Csr& a) {
     a = Csr();
 }
 
-// One pairwise pass: agg_out[n] (pool) and the number of aggregates.
+// One pairwise pass: agg_out[n] (pool, owned by the caller) and the number of aggregates.
 int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cudaStream_t st) {
     nodal_ctx* ctx = h->ctx;
     const int32_t n = A.n;
-    POOL(match, int32_t, n);
-    POOL(best, int32_t, n);
-    POOL(leader, u32, n);
+    Scratch<int32_t> match(ctx, n), best(ctx, n);
+    Scratch<u32> leader(ctx, n);
+    if (!match.ptr || !best.ptr || !leader.ptr) return NODAL_CUDA_ERROR;
     const int grid = rows_grid(ctx, n);
     CUDA_TRY(cudaMemsetAsync(match, 0xFF, sizeof(int32_t) * (size_t)n, st));
     for (int r = 0; r < h->rounds; ++r) {
@@ -342,50 +353,46 @@ int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cu
         amg_accept_kernel<<<grid, AT, 0, st>>>(n, best, match);
         KERNEL_CHECK();
     }
-    int32_t* root = best;
+    int32_t* root = best;       // the proposals are not needed any more
     amg_root_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, root, leader);
     KERNEL_CHECK();
     NODAL_TRY(ctx_reserve(ctx, scan_scratch_bytes(n) + 4096));
     u32* total = carve<u32>(ctx, 16);
     if (!total) return NODAL_CUDA_ERROR;
     NODAL_TRY(scan_exclusive_u32(ctx, leader, leader, n, total, st));
-    int32_t* agg = match;
+    int32_t* agg = match;       // nor is the matching
     amg_assign_kernel<<<grid, AT, 0, st>>>(n, root, leader, agg);
     KERNEL_CHECK();
     u32* total_h = reinterpret_cast<u32*>(ctx->pinned);
     CUDA_TRY(cudaMemcpyAsync(total_h, total, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     *nc_out = (int32_t)total_h[0];
-    *agg_out = agg;
-    ctx_pool_free(ctx, best);
-    ctx_pool_free(ctx, leader);
+    *agg_out = match.keep();
     return NODAL_OK;
 }
 
 // Ac = P^T A P for the piecewise-constant P of `agg`.
 int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* out, cudaStream_t st) {
     nodal_ctx* ctx = h->ctx;
-    POOL(keys, u64, A.nnz);
-    POOL(vals, double, A.nnz);
-    POOL(rhs, double, (size_t)nc + 1);
+    Scratch<u64> keys(ctx, A.nnz);
+    Scratch<double> vals(ctx, A.nnz), rhs(ctx, (size_t)nc + 1);
+    if (!keys.ptr || !vals.ptr || !rhs.ptr) return NODAL_CUDA_ERROR;
     const int cb = bit_length(nc);
     amg_relabel_kernel<<<rows_grid(ctx, A.n), AT, 0, st>>>(A.n, A.indptr, A.indices, A.data, agg, cb,
                                                          keys, vals);
     KERNEL_CHECK();
     int64_t nnzc = 0;
-    NODAL_TRY(nodal_csr_build(ctx, nc, A.nnz, cb, reinterpret_cast<uint64_t*>(keys), vals, rhs, &nnzc, st));
-    POOL(ip, int32_t, (size_t)nc + 1);
-    POOL(ix, int32_t, nnzc);
-    POOL(dv, double, nnzc);
+    NODAL_TRY(nodal_csr_build(ctx, nc, A.nnz, cb, reinterpret_cast<uint64_t*>(keys.ptr), vals, rhs,
+                              &nnzc, st));
+    Scratch<int32_t> ip(ctx, (size_t)nc + 1), ix(ctx, nnzc);
+    Scratch<double> dv(ctx, nnzc);
+    if (!ip.ptr || !ix.ptr || !dv.ptr) return NODAL_CUDA_ERROR;
     NODAL_TRY(nodal_csr_fetch(ctx, nc, nnzc, ip, ix, dv, st));
-    ctx_pool_free(ctx, keys);
-    ctx_pool_free(ctx, vals);
-    ctx_pool_free(ctx, rhs);
     out->n = nc;
     out->nnz = nnzc;
-    out->indptr = ip;
-    out->indices = ix;
-    out->data = dv;
+    out->indptr = ip.keep();
+    out->indices = ix.keep();
+    out->data = dv.keep();
     out->owned = true;
     return NODAL_OK;
 }
@@ -394,27 +401,22 @@ int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* ou
 int transpose_pattern(nodal_amg* h, AmgLevel& L, cudaStream_t st) {
     nodal_ctx* ctx = h->ctx;
     const int32_t n = L.n;
-    POOL(keys, u64, n);
-    POOL(vals, double, n);
-    POOL(rhs, double, (size_t)n + 1);
+    Scratch<u64> keys(ctx, n);
+    Scratch<double> vals(ctx, n), rhs(ctx, (size_t)n + 1), ones(ctx, n);
+    if (!keys.ptr || !vals.ptr || !rhs.ptr || !ones.ptr) return NODAL_CUDA_ERROR;
     const int cb = bit_length(n);
     amg_pt_keys_kernel<<<rows_grid(ctx, n), AT, 0, st>>>(n, L.agg, cb, keys, vals);
     KERNEL_CHECK();
     int64_t cnt = 0;
-    NODAL_TRY(nodal_csr_build(ctx, n, n, cb, reinterpret_cast<uint64_t*>(keys), vals, rhs, &cnt, st));
+    NODAL_TRY(nodal_csr_build(ctx, n, n, cb, reinterpret_cast<uint64_t*>(keys.ptr), vals, rhs, &cnt, st));
     if (cnt != n) {
         nodal_set_error("amg: internal error, P^T has %lld entries for %d rows", (long long)cnt, n);
         return NODAL_CUDA_ERROR;
     }
-    L.pt_ptr = pool<int32_t>(ctx, (size_t)n + 1);
+    L.pt_ptr = pool<int32_t>(ctx, (size_t)n + 1);      // owned by the level from here on
     L.pt_idx = pool<int32_t>(ctx, n);
-    POOL(ones, double, n);
     if (!L.pt_ptr || !L.pt_idx) return NODAL_CUDA_ERROR;
     NODAL_TRY(nodal_csr_fetch(ctx, n, n, L.pt_ptr, L.pt_idx, ones, st));
-    ctx_pool_free(ctx, keys);
-    ctx_pool_free(ctx, vals);
-    ctx_pool_free(ctx, rhs);
-    ctx_pool_free(ctx, ones);
     return NODAL_OK;
 }
 
@@ -422,13 +424,13 @@ int invert_coarsest(nodal_amg* h, const AmgLevel& L, cudaStream_t st) {
     nodal_ctx* ctx = h->ctx;
     const int32_t n = L.n;
     const size_t elems = (size_t)n * 2 * n;
-    POOL(m0, double, elems + 32);
-    POOL(m1, double, elems);
-    int* bad = reinterpret_cast<int*>(m0 + elems);
+    Scratch<double> m0(ctx, elems + 32), m1(ctx, elems);
+    if (!m0.ptr || !m1.ptr) return NODAL_CUDA_ERROR;
+    int* bad = reinterpret_cast<int*>(m0.ptr + elems);
     CUDA_TRY(cudaMemsetAsync(m0, 0, sizeof(double) * (elems + 32), st));
     amg_dense_init_kernel<<<rows_grid(ctx, n), AT, 0, st>>>(n, L.indptr, L.indices, L.data, m0);
     KERNEL_CHECK();
-    double *src = m0, *dst = m1;
+    double *src = m0.ptr, *dst = m1.ptr;
     const int grid = rows_grid(ctx, (int64_t)elems);
     for (int32_t k = 0; k < n; ++k) {
         amg_gj_step_kernel<<<grid, AT, 0, st>>>(n, k, src, dst, bad);
@@ -442,8 +444,6 @@ int invert_coarsest(nodal_amg* h, const AmgLevel& L, cudaStream_t st) {
     int* bad_h = reinterpret_cast<int*>(ctx->pinned);
     CUDA_TRY(cudaMemcpyAsync(bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    ctx_pool_free(ctx, m0);
-    ctx_pool_free(ctx, m1);
     if (*bad_h != 0) {
         nodal_set_error("amg: the coarsest operator is not positive definite (pivot %d of %d); "
                         "the matrix is not SPD", *bad_h, n);
@@ -461,24 +461,33 @@ int build_hierarchy(nodal_amg* h, int32_t n, int64_t nnz, const int32_t* indptr,
         Csr A = cur;            // borrowed view while A is the level operator itself
         A.owned = false;
         int32_t* comp = nullptr;
-        for (int pass = 0; pass < h->passes; ++pass) {
+        int rc = NODAL_OK;
+        for (int pass = 0; pass < h->passes && rc == NODAL_OK; ++pass) {
             int32_t* agg = nullptr;
             int32_t nc = 0;
-            NODAL_TRY(aggregate(h, A, &agg, &nc, st));
             Csr Ac;
-            NODAL_TRY(galerkin(h, A, agg, nc, &Ac, st));
-            if (!comp) comp = agg;
-            else {
+            rc = aggregate(h, A, &agg, &nc, st);
+            if (rc == NODAL_OK) rc = galerkin(h, A, agg, nc, &Ac, st);
+            if (rc == NODAL_OK && comp) {
                 amg_compose_kernel<<<rows_grid(ctx, cur.n), AT, 0, st>>>(cur.n, comp, agg);
-                KERNEL_CHECK();
-                ctx_pool_free(ctx, agg);
+                ++g_nodal_launches;
+                if (cudaGetLastError() != cudaSuccess) {
+                    nodal_set_error("amg: amg_compose_kernel launch failed");
+                    rc = NODAL_CUDA_ERROR;
+                }
             }
+            if (!comp) comp = agg;
+            else ctx_pool_free(ctx, agg);
             free_csr(ctx, A);
             A = Ac;
         }
-        if ((double)A.n > 0.9 * (double)cur.n) {     // coarsening stalled: cur stays the coarsest
-            free_csr(ctx, A);
+        if (rc != NODAL_OK || (double)A.n > 0.9 * (double)cur.n) {
+            free_csr(ctx, A);       // error, or coarsening stalled: cur stays the coarsest level
             ctx_pool_free(ctx, comp);
+            if (rc != NODAL_OK) {
+                free_csr(ctx, cur);
+                return rc;
+            }
             break;
         }
         AmgLevel L;
@@ -487,8 +496,12 @@ int build_hierarchy(nodal_amg* h, int32_t n, int64_t nnz, const int32_t* indptr,
         L.agg = comp;
         L.nc = A.n;
         h->lv.push_back(L);
-        NODAL_TRY(transpose_pattern(h, h->lv.back(), st));
         cur = A;
+        rc = transpose_pattern(h, h->lv.back(), st);
+        if (rc != NODAL_OK) {
+            free_csr(ctx, cur);
+            return rc;
+        }
     }
     AmgLevel L;
     L.n = cur.n; L.nnz = cur.nnz; L.indptr = cur.indptr; L.indices = cur.indices; L.data = cur.data;

@@ -7,7 +7,7 @@ import copy
 import sys
 
 import nodal_b200 as n
-from nodal_b200.cli import load_netlist_or_exit, make_parser
+from nodal_b200.cli import circuit_options, load_netlist_or_exit, make_parser
 
 parser = make_parser(
     "Calculate equivalent resistance using nodal analysis\n"
@@ -68,7 +68,9 @@ def main(argv=None):
     options = parser.parse_args(argv)
     netlist = load_netlist_or_exit(options.netlist_path)
     try:
-        r = equivalent_resistance(netlist, "1", "g", sparse=options.sparse)
+        r = equivalent_resistance(netlist, "1", "g", sparse=options.sparse, **circuit_options(options))
+    except n.UnconnectedCircuitError:
+        sys.exit(1)
     except ValueError:
         print("Invalid netlist\n")
         print("Resistors are the only component allowed in the circuit")

@@ -244,7 +244,11 @@ def test_cli_end_to_end(device, tmp_path, capsys):
         equiv.main([path] + flags)
         out = capsys.readouterr().out.strip()
         assert out.startswith("R = ") and float(out[4:]) == pytest.approx(1.0, rel=1e-9)
+    equiv.main([path, "-s", "--precond", "amg"])             # additions to the reference flags
+    out = capsys.readouterr().out.strip()
+    assert float(out[4:]) == pytest.approx(1.0, rel=1e-9)
     path = write_csv(DOC["unconnected_1.csv"]["rows"], tmp_path / "u1.csv")
-    with pytest.raises(SystemExit) as e:
-        solver.main([path])
-    assert e.value.code == 1
+    for flags in ([], ["-s", "--check-connected"]):
+        with pytest.raises(SystemExit) as e:
+            solver.main([path] + flags)
+        assert e.value.code == 1

@@ -240,6 +240,13 @@ def test_cli_error_paths_without_gpu(tmp_path, capsys):
     assert "not found in netlist" in capsys.readouterr().out
     assert solver.parser.parse_args(["x.csv", "-s"]).sparse is True
     assert equiv.parser.parse_args(["x.csv"]).sparse is False
+    # flags added to the reference command line default to its behaviour
+    from nodal_b200.cli import circuit_options
+    assert circuit_options(solver.parser.parse_args(["x.csv"])) == {}
+    assert circuit_options(solver.parser.parse_args(["x.csv", "-s"])) == {}
+    assert circuit_options(solver.parser.parse_args(["x.csv", "--precond", "amg"])) == {}     # dense: ignored
+    assert circuit_options(equiv.parser.parse_args(["x.csv", "-s", "--precond", "amg", "--check-connected"])) == \
+        {"precond": "amg", "check_connected": True}
 
 
 def test_table_column_scan_is_cached_and_equals_direct_checks():

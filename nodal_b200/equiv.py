@@ -8,6 +8,7 @@ import sys
 
 import nodal_b200 as n
 from nodal_b200.cli import circuit_options, load_netlist_or_exit, make_parser
+from nodal_b200.generators import TableNetlist
 
 parser = make_parser(
     "Calculate equivalent resistance using nodal analysis\n"
@@ -34,6 +35,19 @@ def equivalent_resistance(netlist, a, b, sparse=False, **options):
     missing = [node for node in (a, b) if node != netlist.ground and node not in netlist.nodenum]
     if missing:
         raise KeyError(f"Node `{missing[0]}` not found in netlist")
+
+    if isinstance(netlist, TableNetlist):
+        # Same linear system without touching the table: the 1 A source only contributes the
+        # right-hand side entries +1 at a and -1 at b (models.py:27-32), which
+        # Circuit.port_resistances writes directly.  Appending a row would copy, re-scan and
+        # re-upload the whole table (1.1 GB at 16.7 M nodes) for every call.
+        for node in (a, b):
+            if node == netlist.ground and node != "g":
+                raise KeyError(node)                     # reference: nodenum[ground label], equiv.py:57-59
+        circuit = n.Circuit(netlist, sparse=sparse, **options)
+        (resistance,) = circuit.port_resistances([(a, b)])
+        equivalent_resistance.last_stats = circuit.stats[0]
+        return resistance
 
     probed = copy.deepcopy(netlist)                      # the caller's netlist stays untouched
     probed.process_component([*PROBE, a, b])

@@ -91,6 +91,9 @@ class TableNetlist(Netlist):
 
     @property
     def component_keys(self):
+        if getattr(self, "_component_names", None) is not None:      # Arrow column kept by the ingest
+            from .ingest import _pylist
+            return _pylist(self._component_names)
         f = self._names or (lambda k: f"c{k}")
         return [f(k) for k in range(len(self._table))]
 

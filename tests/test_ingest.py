@@ -88,3 +88,77 @@ def test_speed_on_a_large_file(tmp_path):
     t0 = time.perf_counter(); slow = n.Netlist(path); t1 = time.perf_counter() - t0
     assert dict(fast.nodenum) == slow.nodenum
     assert t_fast < t1          # row-by-row python vs pandas + numpy
+
+
+def test_cli_uses_the_vectorised_ingest_for_large_files(tmp_path):
+    """nodal_b200.cli.load_netlist_or_exit: >= 1 MiB -> TableNetlist with the reference numbering;
+    small or malformed files -> the row-by-row Netlist (which reports errors the reference's way)."""
+    from nodal_b200 import cli
+    from nodal_b200.generators import TableNetlist
+    from oracle import mna_oracle as orc
+    rows = orc.grid2d_rows(160)
+    big = write_csv(rows, tmp_path / "big.csv")
+    import os
+    assert os.path.getsize(big) >= cli.FAST_INGEST_BYTES
+    net = cli.load_netlist_or_exit(big)
+    assert isinstance(net, TableNetlist)
+    ref = orc.OracleNetlist(rows)
+    assert net.ground == ref.ground and dict(net.nodenum) == ref.nodenum and net.nums["kcl"] == ref.kcl
+    small = write_csv(rows[:50], tmp_path / "small.csv")
+    assert not isinstance(cli.load_netlist_or_exit(small), TableNetlist)
+    bad = write_csv(rows + [["rx", "R", "1", "n0_0"]], tmp_path / "bad.csv")      # a row with a missing lead
+    with pytest.raises(ValueError):
+        cli.load_netlist_or_exit(bad)
+    with pytest.raises(SystemExit):
+        cli.load_netlist_or_exit(str(tmp_path / "missing.csv"))
+
+
+def test_value_strings_parse_like_python_float(tmp_path):
+    """Arrow's float parser (fast path) and float() (fallback) give the same bits as the
+    reference's float(value) for every spelling, including the ones Arrow rejects."""
+    rng = np.random.default_rng(3)
+    spellings = [repr(float(v)) for v in rng.uniform(-1e6, 1e6, 300)]
+    spellings += [f"{v:.17g}" for v in 10.0 ** rng.uniform(-300, 300, 300)]
+    spellings += ["1e3", ".5", "5.", "+2", "-0.0", "1E-3", "0.1", "4.9e-324", "1.7976931348623157e308"]
+    rows = [[f"r{k}", "R", s, f"a{k}", "g"] for k, s in enumerate(spellings)]
+    fast = read_table_netlist(write_csv(rows, tmp_path / "arrow.csv"))
+    want = np.array([float(s) for s in spellings])
+    assert np.array_equal(fast.table().value.view(np.uint64), want.view(np.uint64))
+    odd = spellings[:20] + ["1_000", " 7", "8 ", "Infinity"]       # python-only spellings -> fallback for the file
+    rows = [[f"r{k}", "R", s, f"a{k}", "g"] for k, s in enumerate(odd)]
+    p = tmp_path / "python.csv"
+    p.write_text("".join(",".join(r) + "\n" for r in rows))
+    fast = read_table_netlist(str(p))
+    want = np.array([float(s) for s in odd])
+    assert np.array_equal(fast.table().value.view(np.uint64), want.view(np.uint64))
+    same_numbering(str(p))
+    p.write_text("r1,R,abc,1,g\n")
+    with pytest.raises(ValueError, match="expected a number"):
+        read_table_netlist(str(p))
+
+
+@pytest.mark.parametrize("newline", ["\n", "\r\n"])
+def test_line_endings_field_groups_and_lazy_maps(tmp_path, newline):
+    """LF and CRLF files, rows of 5 / 7 / 8 fields interleaved with comments and blank lines, a
+    last line without terminator; the label maps only become dicts when they are used."""
+    lines = ["# c", "r1,R,10,1,2", "", "e1,E,5,2,g", "x1,VCVS,2.5,3,g,1,2", " r2, R, 20, 3, g", "#tail",
+             "f1,CCCS,3,4,g,1,2,r1", "r3,R,7,4,g", "h1,CCVS,2,5,g,2,1,r1", "r4,R,1,5,g"]
+    p = tmp_path / "mixed.csv"
+    p.write_bytes((newline.join(lines)).encode())
+    slow, fast = same_numbering(str(p))
+    t1, t2 = slow.table_and_currents()[0], fast.table_and_currents()[0]
+    for col in ("type", "value", "a", "b", "c", "d", "drv", "branch"):
+        assert np.array_equal(getattr(t1, col), getattr(t2, col)), col
+    big = write_csv(orc.grid2d_rows(40), tmp_path / "lazy.csv")
+    net = read_table_netlist(big)
+    assert net.nodenum._dict is None and net.degrees._dict is None       # nothing built yet
+    assert len(net.nodenum) == net.nums["kcl"] == 40 * 40 - 1
+    assert net.ground == "g" and "g" not in net.nodenum and net.nodenum["1"] >= 0
+    assert net.nodenum._dict is not None
+
+
+def test_ground_is_first_node_of_largest_degree_without_g(tmp_path):
+    rows = [["r1", "R", "1", "a", "b"], ["r2", "R", "1", "c", "b"], ["r3", "R", "1", "c", "d"],
+            ["r4", "R", "1", "d", "a"]] + [[f"s{k}", "R", "1", f"x{k}", f"x{k + 1}"] for k in range(300)]
+    slow, fast = same_numbering(write_csv(rows, tmp_path / "nog.csv"))
+    assert fast.ground == slow.ground == "a"

@@ -13,7 +13,6 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from . import constants as K
 from .table import ComponentTable
 
 

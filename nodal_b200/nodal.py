@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import csv
 import logging
-import os
 import warnings
 
 import numpy as np

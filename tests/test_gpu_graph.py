@@ -7,7 +7,6 @@ from scipy.sparse.csgraph import connected_components
 
 import nodal_b200 as n
 from helpers import golden, write_csv
-from nodal_b200 import constants as K
 from nodal_b200 import generators as gen
 from nodal_b200.table import ComponentTable
 

@@ -106,14 +106,54 @@ def coarsen_level(A, passes=2, rounds=8):
     return agg, Ac
 
 
+def hide_cross_couplings(A, owner):
+    """Copy of A in which couplings between rows of different owners are invisible to the matching
+    (made positive: `_edges` only looks at negative off-diagonals).  Values are NOT used for the
+    Galerkin product -- only for deciding aggregates."""
+    C = A.tocoo()
+    cross = owner[C.row] != owner[C.col]
+    return sps.csr_matrix((np.where(cross, np.abs(C.data), C.data), (C.row, C.col)), shape=A.shape)
+
+
+def coarsen_level_partitioned(A, owner, passes=2, rounds=8):
+    """coarsen_level with rank-local aggregation: no aggregate contains rows of two owners (what a
+    row-partitioned multi-GPU setup computes without communication beyond halo labels).  Returns
+    (agg, Ac, owner of every coarse row); coarse rows of one owner are contiguous."""
+    agg = np.arange(A.shape[0])
+    Ac, own = A, owner
+    for _ in range(passes):
+        a2, na = aggregates(hide_cross_couplings(Ac, own), rounds)
+        Ac = galerkin(Ac, a2, na)
+        coarse_owner = np.zeros(na, dtype=np.int64)
+        coarse_owner[a2] = own
+        own = coarse_owner
+        agg = a2[agg]
+    return agg, Ac, own
+
+
 class AMG:
-    def __init__(self, A, passes=2, coarse=512, omega=0.8, scale=1.8, maxlevels=30, rounds=8, direct_max=2048):
+    """partitions > 1: statement of the multi-GPU hierarchy -- rows are split into `partitions`
+    contiguous blocks (nodal_b200.dist.partition_rows); levels with more than `gather_below` rows
+    aggregate inside the blocks only, smaller levels are aggregated globally (they are replicated
+    on every rank).  partitions == 1 is the single-GPU algorithm of csrc/amg.cu."""
+
+    def __init__(self, A, passes=2, coarse=512, omega=0.8, scale=1.8, maxlevels=30, rounds=8, direct_max=2048,
+                 partitions=1, gather_below=20000):
         self.levels, self.omega, self.scale = [], omega, scale
         A = A.tocsr()
+        n0 = A.shape[0]
+        base, extra = divmod(n0, partitions)
+        bounds = np.cumsum([0] + [base + (1 if k < extra else 0) for k in range(partitions)])
+        owner = np.searchsorted(bounds, np.arange(n0), side="right") - 1
         while A.shape[0] > coarse and len(self.levels) < maxlevels:
-            agg, Ac = coarsen_level(A, passes, rounds)
+            if partitions > 1 and A.shape[0] > gather_below:
+                agg, Ac, next_owner = coarsen_level_partitioned(A, owner, passes, rounds)
+            else:
+                agg, Ac = coarsen_level(A, passes, rounds)
+                next_owner = np.zeros(Ac.shape[0], dtype=np.int64)
             if Ac.shape[0] > 0.9 * A.shape[0]:
                 break
+            owner = next_owner
             P = sps.csr_matrix((np.ones(A.shape[0]), (np.arange(A.shape[0]), agg)), shape=(A.shape[0], Ac.shape[0]))
             self.levels.append((A, P, 1.0 / A.diagonal(), agg))
             A = Ac

@@ -111,3 +111,25 @@ def test_numpy_amg_beats_jacobi_on_irregular_network():
     _, itj = mirror.pcg(A, b, lambda r: dj * r, maxit=20000)
     assert it < itj
     assert np.linalg.norm(b - A @ x) <= 2e-10 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_partitioned_aggregation_statement(world):
+    """Design basis of the multi-GPU AMG: aggregates that never cross a row-partition boundary cost
+    a handful of iterations, coarse rows stay contiguous per owner."""
+    A, b = grid_matrix(128)
+    base = mirror.pcg(A, b, mirror.AMG(A))[1]
+    M = mirror.AMG(A, partitions=world, gather_below=2000)
+    _, it = mirror.pcg(A, b, M)
+    assert it <= base + 8
+    # first level: every aggregate lies inside one block of partition_rows
+    from nodal_b200.dist import partition_rows
+    bounds = partition_rows(A.shape[0], world)
+    owner = np.searchsorted(bounds, np.arange(A.shape[0]), side="right") - 1
+    agg = M.levels[0][3]
+    first_owner = np.full(agg.max() + 1, -1)
+    first_owner[agg[::-1]] = owner[::-1]
+    assert (first_owner[agg] == owner).all()
+    assert (np.diff(first_owner) >= 0).all()            # coarse rows are contiguous per owner
+    # one partition == the plain statement
+    assert mirror.AMG(A, partitions=1).rows == mirror.AMG(A).rows

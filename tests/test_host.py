@@ -312,3 +312,26 @@ def test_solution_bulk_access_and_binary_export(tmp_path):
         assert list(z["nodes"]) == ["a", "b", "zz"] and list(z["branches"]) == ["e1", "e2"]
     text = str(sol)                       # the reference layout is untouched
     assert text.splitlines()[0] == "Ground node: g" and "e(zz) \t= 0.25" in text and "i(e2) \t= -4.0" in text
+
+
+def test_equivalent_resistance_argument_errors_need_no_gpu(tmp_path):
+    """ValueError / KeyError of equiv.py:43-48 are raised before anything touches the device, for the
+    single-pair and the many-port call, for dict netlists and table netlists."""
+    from nodal_b200 import equiv
+    from nodal_b200 import generators as gen
+    mixed = n.Netlist(write_csv(DOC["1.6.1.csv"]["rows"], tmp_path / "mixed.csv"))
+    with pytest.raises(ValueError, match="not resistive"):
+        equiv.equivalent_resistances(mixed, [("1", "g")])
+    grid = gen.grid2d(8)
+    for call in (lambda: equiv.equivalent_resistance(grid, "1", "nowhere", sparse=True),
+                 lambda: equiv.equivalent_resistances(grid, [("1", "g"), ("nowhere", "g")])):
+        with pytest.raises(KeyError, match="nowhere"):
+            call()
+    # a table netlist whose ground is not called "g": the reference indexes nodenum with the ground
+    # label and fails with KeyError (equiv.py:57-59); the table fast path keeps that
+    rows = [["r1", "R", "1", "a", "b"], ["r2", "R", "1", "b", "c"], ["r3", "R", "1", "b", "d"]]
+    from nodal_b200.ingest import read_table_netlist
+    tn = read_table_netlist(write_csv(rows, tmp_path / "nog.csv"))
+    assert tn.ground == "b"
+    with pytest.raises(KeyError):
+        equiv.equivalent_resistance(tn, "a", "b")

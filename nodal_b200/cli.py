@@ -39,6 +39,9 @@ FAST_INGEST_BYTES = 1 << 20
 def load_netlist_or_exit(path):
     """Exit status 1 when the file does not exist (the error itself is logged by Netlist)."""
     try:
+        if os.path.isfile(path) and str(path).endswith(".npz"):      # binary form, see ingest.save_table_netlist
+            from nodal_b200.ingest import load_table_netlist
+            return load_table_netlist(path)
         if os.path.isfile(path) and os.path.getsize(path) >= FAST_INGEST_BYTES:
             from nodal_b200.ingest import read_table_netlist
             try:

@@ -162,3 +162,43 @@ def test_ground_is_first_node_of_largest_degree_without_g(tmp_path):
             ["r4", "R", "1", "d", "a"]] + [[f"s{k}", "R", "1", f"x{k}", f"x{k + 1}"] for k in range(300)]
     slow, fast = same_numbering(write_csv(rows, tmp_path / "nog.csv"))
     assert fast.ground == slow.ground == "a"
+
+
+@pytest.mark.parametrize("source", ["doc", "c3", "grid_generator", "dict_netlist"])
+def test_binary_round_trip(source, tmp_path):
+    """save_table_netlist / load_table_netlist: same table, numbering, names and currents."""
+    from nodal_b200.ingest import load_table_netlist, save_table_netlist
+    if source == "doc":
+        net = read_table_netlist(write_csv(DOC["test_1.csv"]["rows"], tmp_path / "t.csv"))
+    elif source == "c3":
+        net = read_table_netlist(write_csv(gen.random_opamp_network_rows(M=150, P=12, S=10, V=5, seed=2),
+                                           tmp_path / "c3.csv"))
+    elif source == "grid_generator":
+        net = gen.grid2d(25)
+    else:
+        net = n.Netlist(write_csv(DOC["netlist.csv"]["rows"], tmp_path / "n.csv"))
+    path = tmp_path / "net.npz"
+    save_table_netlist(net, path)
+    back = load_table_netlist(path)
+    t1, c1 = net.table_and_currents()
+    t2, c2 = back.table_and_currents()
+    for col in ("type", "value", "a", "b", "c", "d", "drv", "branch"):
+        assert np.array_equal(getattr(t1, col), getattr(t2, col)), col
+    assert (t1.kcl, t1.be) == (t2.kcl, t2.be) and list(c1) == list(c2)
+    assert back.ground == net.ground
+    assert dict(back.nodenum) == dict(net.nodenum) and list(back.nodenum) == list(net.nodenum)
+    assert back.anomnum == dict(net.anomnum)
+    assert list(back.component_keys) == list(net.component_keys)
+    assert back.nums["kcl"] == net.nums["kcl"] and back.nums["components"] == len(t1)
+
+
+def test_convert_and_load_through_the_cli(tmp_path, capsys):
+    from nodal_b200 import cli, ingest
+    src = write_csv(orc.grid2d_rows(12), tmp_path / "g.csv")
+    dst = str(tmp_path / "g.npz")
+    ingest.main([src, dst])
+    assert "ground 'g'" in capsys.readouterr().out
+    net = cli.load_netlist_or_exit(dst)
+    ref = n.Netlist(src)
+    assert dict(net.nodenum) == ref.nodenum and net.ground == ref.ground
+    assert net.is_resistive()

@@ -35,15 +35,68 @@ KNIGHT_LIMIT = 4 / np.pi - 0.5       # infinite-grid knight's-move resistance
 
 
 # --------------------------------------------------------------------------- reference arm
-def oracle_step(N):
-    """The reference's own path on the host (oracle port: csv-row numbering, per-item scipy
-    DOK stamping, spsolve) on an N x N grid.  Returns (seconds, unknowns, R)."""
-    from oracle import mna_oracle as orc
-    rows = orc.grid2d_rows(N)
-    t0 = time.perf_counter()
-    r = orc.equivalent_resistance(rows, "1", "g", sparse=True, backend="dok")
-    dt = time.perf_counter() - t0
-    return dt, N * N - 1, r
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def grid_csv(N):
+    """The N x N grid netlist as the csv FILE the reference reads (written outside any timed region)."""
+    import csv
+    import tempfile
+    from oracle import mna_oracle as orc            # generator of the rows only
+    fd, path = tempfile.mkstemp(prefix=f"grid{N}_", suffix=".csv")
+    with os.fdopen(fd, "w", newline="") as fh:
+        csv.writer(fh).writerows(orc.grid2d_rows(N))
+    return path
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_DIR, "nodal", "nodal.py"))
+
+
+def reference_step(N, path=None):
+    """One pass of the hot path on the host CPU over an N x N grid: csv file -> Netlist ->
+    equivalent_resistance(..., sparse=True) (numbering, deepcopy, per-item DOK stamping, spsolve).
+    Runs the UNMODIFIED reference from baseline/_ref (baseline/install_ref.py) when it is there
+    (kind "reference"), else the oracle port of the same algorithm (kind "port").
+    Returns (seconds, unknowns, R, kind)."""
+    own = path is None
+    if own:
+        path = grid_csv(N)
+    try:
+        if reference_available():
+            if REF_DIR not in sys.path:
+                sys.path.insert(0, REF_DIR)
+            import logging
+            import nodal as ref                      # the reference package, not this repo's
+            import nodal.equiv
+            logging.getLogger().setLevel(logging.ERROR)
+            t0 = time.perf_counter()
+            net = ref.Netlist(path)
+            r = ref.equiv.equivalent_resistance(net, "1", "g", sparse=True)
+            dt = time.perf_counter() - t0
+            return dt, N * N - 1, float(r), "reference"
+        from oracle import mna_oracle as orc
+        import csv
+        t0 = time.perf_counter()
+        with open(path) as fh:
+            rows = [row for row in csv.reader(fh, skipinitialspace=True)]
+        r = orc.equivalent_resistance(rows, "1", "g", sparse=True, backend="dok")
+        dt = time.perf_counter() - t0
+        return dt, N * N - 1, float(r), "port"
+    finally:
+        if own:
+            os.unlink(path)
+
+
+def cpu_baseline_entry(N, dt, unknowns, r, kind, full_grid):
+    what = ("the unmodified reference package (baseline/_ref): Netlist(csv) + equivalent_resistance(sparse=True)"
+            if kind == "reference" else
+            "oracle port of the reference algorithm (csv rows -> numbering -> per-item scipy DOK stamping -> spsolve)")
+    return {"value": unknowns / dt, "unit": "unknowns/s", "cores": 1, "kind": kind,
+            "sample": f"{N}x{N} grid ({unknowns} unknowns) through {what} in {dt:.1f} s, R={r!r}; single-threaded "
+                      f"by construction (Python stamping loop + SuperLU); the full {full_grid}x{full_grid} workload "
+                      f"cannot run on this path (SuperLU MemoryError, BASELINE.md 2.2)",
+            "host_cpus": os.cpu_count(), "seconds": dt, "grid": N}
 
 
 def run_reference(args):
@@ -51,28 +104,30 @@ def run_reference(args):
     if rank != 0:
         return
     N = args.ref_grid
-    for _ in range(args.warmup):
-        oracle_step(max(20, N // 4))
-    times = []
-    for _ in range(args.steps):
-        dt, unknowns, r = oracle_step(N)
-        times.append(dt)
+    small = grid_csv(max(20, N // 8))
+    path = grid_csv(N)
+    try:
+        for _ in range(args.warmup):
+            reference_step(max(20, N // 8), small)
+        times = []
+        for _ in range(args.steps):
+            dt, unknowns, r, kind = reference_step(N, path)
+            times.append(dt)
+    finally:
+        os.unlink(small)
+        os.unlink(path)
     total = sum(times)
     value = args.steps * unknowns / total
-    cores = 1
     line = {
         "impl": "reference", "metric": "unknowns_per_second", "value": value, "unit": "unknowns/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"grid2d_{args.grid}x{args.grid} equivalent resistance (config C5a)",
-                   "sample": f"grid2d_{N}x{N}"},
-        "cpu_baseline": {"value": value, "unit": "unknowns/s", "cores": cores, "kind": "port",
-                         "sample": f"{N}x{N} grid ({unknowns} unknowns): oracle port of Netlist numbering + "
-                                   f"per-item scipy DOK stamping + spsolve, R={r!r}; the reference cannot run "
-                                   f"the full {args.grid}^2 workload (SuperLU MemoryError, BASELINE.md 2.2)"},
+                   "sample": f"grid2d_{N}x{N}", "warmup_sample": f"grid2d_{max(20, N // 8)}"},
+        "cpu_baseline": cpu_baseline_entry(N, total / args.steps, unknowns, r, kind, args.grid),
         "e2e": {"value": value, "unit": "unknowns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "host_cpus": os.cpu_count(),
+        "host_cpus": os.cpu_count(), "R": r,
     }
     print(json.dumps(line), flush=True)
 
@@ -310,15 +365,32 @@ def run_ours(args):
             amg = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     solve_ms = info.get("solve_ms", ms_per_step)
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
-    cpu = None
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only), and the SAME sample through this
+    # repo from the same csv file with the same call sequence (file -> netlist -> equivalent_resistance):
+    # a like-for-like pair next to the headline, whose CPU arm cannot run the full size
+    cpu, same = None, None
     if world == 1 and not args.no_cpu_baseline:
-        dt, unk, r_cpu = oracle_step(args.ref_grid)
-        cpu = {"value": unk / dt, "unit": "unknowns/s", "cores": 1, "kind": "port",
-               "sample": f"{args.ref_grid}x{args.ref_grid} grid ({unk} unknowns) through the oracle port "
-                         f"(per-item scipy DOK stamping + SuperLU spsolve) in {dt:.1f} s, R={r_cpu!r}; "
-                         f"the {N}x{N} workload cannot run on the CPU path (SuperLU MemoryError)",
-               "host_cpus": os.cpu_count()}
+        from nodal_b200 import cli
+        import nodal_b200.equiv
+        Ns = args.ref_grid
+        path = grid_csv(Ns)
+        try:
+            def gpu_from_csv():
+                net = cli.load_netlist_or_exit(path)          # what nodal-resistance FILE -s does
+                return float(n.equiv.equivalent_resistance(net, "1", "g", sparse=True))
+            gpu_from_csv()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r_gpu = gpu_from_csv()
+            torch.cuda.synchronize()
+            t_gpu = time.perf_counter() - t0
+            dt, unk, r_cpu, kind = reference_step(Ns, path)
+        finally:
+            os.unlink(path)
+        cpu = cpu_baseline_entry(Ns, dt, unk, r_cpu, kind, N)
+        same = {"grid": Ns, "unknowns": unk, "what": "csv file -> netlist -> equivalent_resistance(sparse=True), "
+                "host numbering / ingest included on both sides", "gpu_s": t_gpu, "cpu_s": dt, "cpu_kind": kind,
+                "speedup": dt / t_gpu, "R_gpu": r_gpu, "R_cpu": r_cpu, "R_rel_diff": abs(r_gpu - r_cpu) / abs(r_cpu)}
 
     line = {
         "metric": "unknowns_per_second", "value": value, "unit": "unknowns/s", "n_gpus": world,
@@ -335,7 +407,7 @@ def run_ours(args):
         "dist_breakdown_ms": {k: info[k] for k in ("assemble_wall_ms", "solve_wall_ms", "host_ms", "comm") if k in info},
         "pcg_achieved_gbs": pcg_bytes / (solve_ms * 1e-3) / 1e9 if world == 1 else None,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
-        "cpu_baseline": cpu, "amg_pcg_opt_in": amg,
+        "cpu_baseline": cpu, "same_size_pair": same, "amg_pcg_opt_in": amg,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -124,9 +124,14 @@ lu_panel_kernel(double* __restrict__ A, int n, int k, int jb, int rows_per_cta, 
         }
         __syncthreads();
         const double pv_abs = s_val[1];
-        const int pv_row = s_row[1], pv_cta = s_cta[1];
+        // No candidate at all (every entry at or below the diagonal is NaN: better() never picks
+        // one): keep row g where it is -- the swap is a no-op, info is flagged below and the NaNs
+        // propagate into the solution as LAPACK's do -- instead of electing row INT_MAX.
+        const bool none = !(pv_abs >= 0.0);
+        const int pv_row = none ? g : s_row[1], pv_cta = s_cta[1];
         for (int c = tid; c < jb; c += PANEL_THREADS)
-            prow[c] = __ldcg(&candrow[((size_t)par * ncta + pv_cta) * LU_NB + c]);
+            prow[c] = none ? __ldcg(&diagrow[(size_t)par * LU_NB + c])
+                           : __ldcg(&candrow[((size_t)par * ncta + pv_cta) * LU_NB + c]);
         if (blockIdx.x == 0 && tid == 0) {
             ipiv[g] = pv_row;
             if (!(pv_abs > 0.0)) atomicCAS(info, 0, g + 1);   // exact zero (or NaN) pivot
@@ -175,7 +180,7 @@ lu_swap_rows_kernel(double* __restrict__ A, int n, int k, int jb, const int* __r
         const int c = t < k ? t : t + jb;
         for (int j = 0; j < jb; ++j) {
             const int r1 = k + j, r2 = ipiv[r1];
-            if (r2 != r1) {
+            if (r2 != r1 && r2 >= 0 && r2 < n) {
                 const double a = A[(size_t)r1 * n + c], b = A[(size_t)r2 * n + c];
                 A[(size_t)r1 * n + c] = b;
                 A[(size_t)r2 * n + c] = a;

@@ -35,6 +35,10 @@ from .table import ComponentTable
 NCOLS = 8          # name, type, value, anode, bnode, pos_control, neg_control, driver
 
 
+class DuplicateNameError(ValueError):
+    """Two rows share a component name: only the row-by-row Netlist reproduces the reference."""
+
+
 def _arrow():
     import pyarrow as pa
     import pyarrow.compute as pc
@@ -270,6 +274,16 @@ def read_table_netlist(path):
                                                 for c, col in enumerate((name, kind, value, a, b, c_, d_, drv)))
         m = len(name)
         kcodes, kuniq = type_codes(kind)               # again: OPMODEL rows were replaced
+    # ---- duplicate component names: the reference keeps ONE record per name (the last row wins,
+    # nodal.py:243) and stamps it once per occurrence, with the branch number of the last
+    # anomalous occurrence.  That is not a per-row table any more: refuse, so that callers
+    # (cli.load_netlist_or_exit) fall back to the row-by-row Netlist, which reproduces it.
+    if m:
+        ncodes = _numpy(pc.dictionary_encode(name).indices, np.int32)
+        if int(ncodes.max()) + 1 != m:
+            first = np.flatnonzero(np.bincount(ncodes, minlength=m)[ncodes] > 1)[0]
+            raise DuplicateNameError(f"component name {label(name, first)!r} is used more than once; "
+                                     "use nodal_b200.Netlist (row by row) for this file")
     val = _to_float(value, name) if m else np.zeros(0)
     # ---- first-appearance node numbering (nodal.py:249-257): anode, then bnode, per component
     if m:

@@ -113,6 +113,9 @@ def main():
             ["f1", "CCCS", "3", "3", "g", "1", "2", "r1"], ["r3", "R", "5", "3", "g"],
             ["q1", "OPMODEL", "1000", "4", "g", "3", "5"], ["r4", "R", "500", "5", "g"],
             ["r5", "R", "100", "4", "g"]],
+        "x_duplicate_name.csv": [      # components[key] is overwritten (nodal.py:243): last row wins,
+            ["r1", "R", "10", "a", "g"], ["r1", "R", "20", "b", "a"],   # stamped once per occurrence
+            ["r2", "R", "5", "b", "g"], ["a1", "A", "1", "b", "g"]],
         "x_negative_resistor.csv": [   # g + (-g) passes through exact zero then re-inserts
             ["r1", "R", "2", "1", "g"], ["r2", "R", "-2", "1", "g"], ["r3", "R", "4", "1", "g"],
             ["r4", "R", "1", "1", "2"], ["r5", "R", "1", "2", "g"], ["a1", "A", "1", "2", "g"]],

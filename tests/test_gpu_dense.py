@@ -65,8 +65,31 @@ def test_lu_singular_reports_pivot(device):
     assert info["status"] == _lib.SINGULAR and info["info"] == 1
 
 
+def test_lu_nan_input_does_not_fault(device):
+    """A NaN component value ('nan' passes float()) must give NaNs / a flagged pivot like LAPACK,
+    not an out-of-bounds row swap (n > 128 takes the multi-panel path)."""
+    m = 300
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((m, m)) + 4 * np.eye(m)
+    A[37, :] = np.nan
+    A[:, 211] = np.nan
+    x, info = lu(device, A, rng.standard_normal(m))
+    assert info["status"] in (0, _lib.SINGULAR)
+    assert np.isnan(x).any()
+    # the device is still healthy: the next solve is exact
+    B = rng.standard_normal((m, m)) + 4 * np.eye(m)
+    b = rng.standard_normal(m)
+    y, info = lu(device, B, b)
+    assert info["status"] == 0 and normwise(y, np.linalg.solve(B, b)) < 1e-10
+    # all-NaN matrix: every panel column has no candidate at all
+    x, info = lu(device, np.full((m, m), np.nan), b)
+    assert np.isnan(x).all()
+    y, info = lu(device, B, b)
+    assert info["status"] == 0 and normwise(y, np.linalg.solve(B, b)) < 1e-10
+
+
 @pytest.mark.parametrize("name", sorted(k for k, v in DOC.items() if "result_dense" in v))
-def test_doc_netlists_dense_solve(device, name, tmp_path):
+def test_doc_netlists_dense_solve(device, name, tmp_path, capsys):
     g = DOC[name]
     net = n.Netlist(write_csv(g["rows"], tmp_path / name))
     sol = n.Circuit(net).solve()
@@ -75,6 +98,24 @@ def test_doc_netlists_dense_solve(device, name, tmp_path):
     # 1 V potentials, where the reference itself moves by 3e-6 between LAPACK builds
     assert normwise(sol.result, want) < 1e-9
     G, A = np.array(g["G"]), np.array(g["A"])
+    # block-normwise: potentials and branch currents separately.  A backward
+    # stable solve bounds the WHOLE-vector error by ~cond * eps * |x|; a block whose entries are
+    # tiny next to the rest (1e-12 A currents beside 1 V potentials) only inherits that absolute
+    # error, so its relative bound is cond * eps * |x|_inf / |x_block|_inf (floor 1e-9).
+    kcl = len(net.nodenum)
+    cond = np.linalg.cond(G)
+    got = np.asarray(sol.result, float)
+    report = []
+    for label, blk in (("potentials", slice(0, kcl)), ("currents", slice(kcl, None))):
+        if want[blk].size == 0:
+            continue
+        scale = np.max(np.abs(want[blk]))
+        err = np.max(np.abs(got[blk] - want[blk])) / (scale if scale > 0 else 1.0)
+        bound = max(1e-9, 8 * cond * np.finfo(float).eps * np.max(np.abs(want)) / (scale if scale > 0 else 1.0))
+        report.append(f"{label} {err:.2e} (bound {bound:.2e})")
+        assert err <= bound, (name, label, err, bound, cond)
+    with capsys.disabled():
+        print(f"\n[{name}] cond {cond:.2e} block-normwise error: " + ", ".join(report))
     assert np.linalg.norm(G @ sol.result - A) <= 1e-10 * max(np.linalg.norm(A), 1e-300) + 1e-9 * 0
     text = str(sol).splitlines()
     ref = g["printed"].splitlines()

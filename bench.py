@@ -2,15 +2,19 @@
 """Headline benchmark: equivalent-resistance solve of a 16M-node resistor grid (config C5a).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 4096]
+                    [--precond amg|jacobi]
 
-One "step" is one pass of the hot path over the workload: stamp the component table ->
-build the CSR -> Jacobi-PCG to relres 1e-10 -> R = e(1) - e(g).
+One "step" is one pass of the hot path over the workload: (N > 1: select the rank's components
+on the device ->) stamp the component table -> build the CSR -> AMG-preconditioned CG (default;
+--precond jacobi = the round-1 headline) to relres 1e-10 -> R = e(1) - e(g).  The same algorithm
+runs on every GPU count (rows partitioned over the ranks).
   value : unknowns / s with the component table already resident in HBM
-  e2e   : the same through the public API with HOST buffers (pinned table H2D and result
-          vector D2H inside the timed region)
-  roofline : the PCG's SpMV(+dot) kernel, algorithmic bytes 12 nnz + 20 n per launch
-  cpu_baseline : the CPU oracle (reference algorithm: Python DOK stamping + scipy spsolve)
-          on a bounded sample of the same workload
+  e2e   : the same through the public API with HOST buffers (pinned table H2D and the whole
+          solution vector D2H inside the timed region, on every rank)
+  roofline : the level-0 SELL sweep of the AMG cycle (Jacobi: the PCG's SpMV + dot kernel),
+          per-launch time from CUDA events, algorithmic bytes in DESIGN.md
+  cpu_baseline : the unmodified reference (baseline/_ref; oracle port if absent) on a bounded
+          sample of the same workload; same_size_pair: that sample through this repo as well
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -29,8 +33,17 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 import numpy as np  # noqa: E402
 
 RTOL = 1e-10
-# DRAM traffic of one pcg_spmv_dot_sell_kernel launch from the committed ncu capture (grid side -> bytes)
-NCU_DRAM_BYTES_PER_LAUNCH = {4096: 1.143079e9 + 0.128681e9}
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full) of the roofline kernels,
+# read from the committed capture summaries: profiles/ncu_traffic.json = {kernel: {grid side: bytes, "source": csv}}
+def ncu_traffic(kernel, N):
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            entry = json.load(fh).get(kernel, {})
+        return entry.get(str(N))
+    except (OSError, ValueError):
+        return None
+
+
 KNIGHT_LIMIT = 4 / np.pi - 0.5       # infinite-grid knight's-move resistance
 
 
@@ -192,6 +205,7 @@ def run_ours(args):
     import torch.distributed as dist
     import nodal_b200 as n
     from nodal_b200 import _lib
+    from nodal_b200 import dist as ndist
     from nodal_b200 import generators as gen
     from nodal_b200.device import Device
 
@@ -204,6 +218,8 @@ def run_ours(args):
     dev = Device.get(local)
     lib = dev.lib
     N = args.grid
+    precond = args.precond
+    amg_opts = {"gather_below": args.gather_below} if args.gather_below else {}
 
     # ---- workload (host, untimed): grid netlist + the 1 A probe source of equivalent_resistance
     import copy
@@ -211,29 +227,27 @@ def run_ours(args):
     probe = copy.deepcopy(net)
     probe.process_component(["a1", "A", "1", "1", "g"])      # equiv.py:51
     table = probe.table()
+    table.facts()                                             # the host scan of the columns (cached with the table)
     n_unknowns, ncomp = table.n, len(table)
     row_1 = probe.nodenum["1"]
 
-    if world > 1:
-        from nodal_b200 import dist as ndist
-        runner = ndist.GridRunner(dev, table, row_1, rank, world, rtol=RTOL)
-    else:
-        runner = None
-
-    dtab = dev.upload_table(table)                            # resident in HBM for the `value` leg
+    # value leg: the whole component table resident in HBM on every rank; one step = (N > 1: select the
+    # rank's components on the device) + stamp + CSR build of the rank's rows + partitioned solve + R
+    classic_jacobi = world == 1 and precond == "jacobi"      # the tuned single-GPU Jacobi-PCG of round 1
+    runner = None
+    if not classic_jacobi:
+        runner = ndist.GridRunner(dev, table, row_1, rank, world, rtol=RTOL, precond=precond, amg=amg_opts,
+                                  solver=ndist.shared_solver(dev, rank, world))
+    dtab = dev.upload_table(table)
     torch.cuda.synchronize()
 
     def step_device():
         if runner is not None:
             return runner.step(dtab)
         csr, rhs = dev.assemble_csr(table, dtab=dtab)
-        if args.precond == "amg":
-            x, info = dev.amg_pcg(csr, rhs, rtol=RTOL)
-        else:
-            x, info = dev.pcg(csr, rhs, rtol=RTOL)
-        r = float(x[row_1])                                   # e(1) - e(g), ground is 0 V
+        x, info = dev.pcg(csr, rhs, rtol=RTOL)
         info["nnz"] = csr.nnz
-        return r, info
+        return float(x[row_1]), info                          # e(1) - e(g), ground is 0 V
 
     def barrier():
         if world > 1:
@@ -247,10 +261,11 @@ def run_ours(args):
     launches0 = lib.nodal_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    iters = []
+    iters, infos = [], []
     for _ in range(args.steps):
         r, info = step_device()
         iters.append(info["iterations"])
+        infos.append(info)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -264,106 +279,105 @@ def run_ours(args):
     value = n_unknowns / (ms_per_step * 1e-3)
     nnz = info["nnz"]
 
-    # ---- e2e leg: public API, host buffers (pinned), H2D + D2H inside the timed region
-    e2e = None
-    if world == 1:
-        table.pin_memory()                      # host buffers of the public API call, page-locked
-        h2d = table.nbytes
-
-        def step_e2e():
-            # the call a user makes (nodal/nodal.py:8-13): host netlist in, host result vector out
-            sol = n.Circuit(probe, sparse=True, rtol=RTOL, precond=args.precond).solve()
-            return float(sol.result[row_1]), sol.stats
-
-        step_e2e()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ev0.record()
-        for _ in range(args.steps):
-            r_e2e, _ = step_e2e()
-        ev1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        e2e_ms = max(ev0.elapsed_time(ev1), wall * 1e3) / args.steps
-        e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_unknowns * 8),
-               "ms_per_step": e2e_ms, "R": r_e2e,
-               "api": "nodal_b200.Circuit(netlist, sparse=True).solve() on a host TableNetlist (pinned columns)"}
-
+    # ---- e2e leg: the public API with HOST buffers.  Every rank holds the netlist (pinned columns):
+    # Circuit(netlist, sparse=True[, distributed=True]).solve() uploads the table, (selects the rank's
+    # components on the device,) assembles, solves and brings the whole solution vector back to the
+    # host of every rank.
+    table.pin_memory()
+    opts = dict(rtol=RTOL, precond=precond)
     if world > 1:
-        runner.step_e2e()
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            r_e2e, _ = runner.step_e2e()
-        ev1.record()
-        barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        opts["distributed"] = True
+    if amg_opts and precond != "jacobi":
+        opts["amg"] = amg_opts
+
+    def step_e2e():
+        sol = n.Circuit(probe, sparse=True, **opts).solve()   # the call a user makes (nodal/nodal.py:8-13)
+        return float(sol.result[row_1]), sol.stats
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        r_e2e, e2e_stats = step_e2e()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(ev0.elapsed_time(ev1), wall * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        hb = torch.tensor([float(runner.local.nbytes), float(runner._host_x.numel() * 8)], device="cuda",
-                          dtype=torch.float64)
-        dist.all_reduce(hb)
-        e2e_ms = float(t.item()) / args.steps
-        e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
-               "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()),
-               "ms_per_step": e2e_ms, "R": r_e2e,
-               "api": "nodal_b200.dist.GridRunner.step_e2e(): per-rank pinned component table up, "
-                      "per-rank slice of the solution down (bytes summed over ranks)"}
+        e2e_ms = float(t.item())
+    e2e_ms /= args.steps
+    e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
+           "h2d_bytes_per_step": int(table.nbytes) * world, "d2h_bytes_per_step": int(n_unknowns * 8) * world,
+           "ms_per_step": e2e_ms, "R": r_e2e, "solver": e2e_stats.get("solver"),
+           "api": "nodal_b200.Circuit(netlist, sparse=True" + (", distributed=True" if world > 1 else "") +
+                  ").solve() on a host TableNetlist (pinned columns) on every rank: whole table up, whole solution "
+                  "vector down, per rank (bytes summed over ranks)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (PCG SpMV + dot), per-launch time from CUDA events
+
+    # ---- roofline of the dominant kernel, per-launch time from CUDA events (rank 0, one GPU's share)
     peak, peak_src = load_peaks()
-    roof = None
+    roof, amg_side, jac_side = None, None, None
     if world == 1:
         csr, rhs = dev.assemble_csr(table, dtab=dtab)
-        _, prof = dev.pcg(csr, rhs, rtol=RTOL, maxit=256, flags=_lib.PCG_PROFILE)
-        km = prof.get("kernel_ms")
-        if km:
-            bytes_spmv = 12.0 * nnz + 20.0 * n_unknowns
-            achieved = bytes_spmv / (km["spmv_dot"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "pcg_spmv_dot_sell_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(N),
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
-                                      "profiles/r1_pcg_kernels_ncu_full_raw.csv" if N in NCU_DRAM_BYTES_PER_LAUNCH else None,
-                    "algorithmic_bytes_per_launch": bytes_spmv, "ms_per_launch": km["spmv_dot"],
-                    "samples": km["samples"],
-                    "other_kernels_ms": {"update": km["update"], "direction": km["direction"]},
+        if precond == "jacobi":
+            _, prof = dev.pcg(csr, rhs, rtol=RTOL, maxit=256, flags=_lib.PCG_PROFILE)
+            km = prof.get("kernel_ms")
+            if km:
+                bytes_spmv = 12.0 * nnz + 20.0 * n_unknowns
+                achieved = bytes_spmv / (km["spmv_dot"] * 1e-3) / 1e9
+                roof = {"bound": "hbm", "kernel": "pcg_spmv_dot_sell_kernel", "achieved": achieved, "peak": peak,
+                        "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                        "traffic": ncu_traffic("pcg_spmv_dot_sell_kernel", N),
+                        "algorithmic_bytes_per_launch": bytes_spmv, "ms_per_launch": km["spmv_dot"],
+                        "samples": km["samples"],
+                        "other_kernels_ms": {"update": km["update"], "direction": km["direction"]},
+                        "frac_of_nominal_8TBs": achieved / 8000.0}
+        else:
+            # level-0 SELL sweeps of the AMG-PCG step: 3 per iteration (CG q = A p, residual of the pre-smoothed
+            # iterate, post-smoothing sweep).  Algorithmic bytes: 12 nnz (value + column) + per row the gathered
+            # vector once (8), the right-hand side (8), the diagonal (8, Jacobi sweep only) and the result (8).
+            h = dev.amg(csr)
+            km = h.profile_sweeps(reps=64)
+            h.close()
+            by = {"jacobi": 12.0 * nnz + 32.0 * n_unknowns, "residual": 12.0 * nnz + 24.0 * n_unknowns,
+                  "spmv_dot": 12.0 * nnz + 16.0 * n_unknowns}
+            achieved = by["jacobi"] / (km["jacobi"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "amg_sell_kernel<2> (level-0 damped-Jacobi sweep)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": ncu_traffic("amg_sell_kernel<2>", N),
+                    "algorithmic_bytes_per_launch": by["jacobi"], "ms_per_launch": km["jacobi"], "samples": 64,
+                    "other_kernels_ms": {"level0_residual_sweep": km["residual"], "level0_spmv_dot": km["spmv_dot"]},
+                    "other_kernels_gbs": {"level0_residual_sweep": by["residual"] / km["residual"] / 1e6,
+                                          "level0_spmv_dot": by["spmv_dot"] / km["spmv_dot"] / 1e6},
                     "frac_of_nominal_8TBs": achieved / 8000.0}
-    pcg_bytes = (12.0 * nnz + 108.0 * n_unknowns) * float(np.mean(iters))
-
-    # ---- the opt-in AMG-preconditioned solve on the same system (one warm-up + one timed step;
-    # reported beside the headline, never part of it)
-    amg = None
-    if world == 1 and args.precond == "jacobi" and not args.no_amg:
-        try:
-            for _ in range(2):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                csr, rhs = dev.assemble_csr(table, dtab=dtab)
-                xa, ia = dev.amg_pcg(csr, rhs, rtol=RTOL)
-                ra = float(xa[row_1])
-                torch.cuda.synchronize()
-                wall = (time.perf_counter() - t0) * 1e3
-            amg = {"ms_per_step": wall, "setup_ms": ia["setup_ms"], "solve_ms": ia["solve_ms"],
-                   "iterations": ia["iterations"], "relres": ia["relres"], "status": ia["status"], "R": ra,
-                   "levels": ia["level_rows"], "operator_complexity": ia["operator_complexity"],
-                   "R_rel_diff_vs_jacobi": abs(ra - r) / abs(r)}
-            # the same through the public API with host buffers (pinned columns up, solution down)
-            for _ in range(2):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                sol = n.Circuit(probe, sparse=True, rtol=RTOL, precond="amg").solve()
-                ra_e2e = float(sol.result[row_1])
-                torch.cuda.synchronize()
-                wall = (time.perf_counter() - t0) * 1e3
-            amg["e2e_ms_per_step"] = wall
-            amg["e2e_R"] = ra_e2e
-        except Exception as exc:      # the headline line must not depend on the opt-in path
-            amg = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    solve_ms = info.get("solve_ms", ms_per_step)
+        # ---- the other preconditioner on the same system, beside the headline (one warm-up + one timed step)
+        if not args.no_side:
+            try:
+                for _ in range(2):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    csr, rhs = dev.assemble_csr(table, dtab=dtab)
+                    xa, ia = (dev.pcg(csr, rhs, rtol=RTOL) if precond != "jacobi" else dev.amg_pcg(csr, rhs, rtol=RTOL))
+                    ra = float(xa[row_1])
+                    torch.cuda.synchronize()
+                    wall = (time.perf_counter() - t0) * 1e3
+                side = {"ms_per_step": wall, "setup_ms": ia["setup_ms"], "solve_ms": ia["solve_ms"],
+                        "iterations": ia["iterations"], "relres": ia["relres"], "status": ia["status"], "R": ra,
+                        "R_rel_diff_vs_headline": abs(ra - r) / abs(r)}
+                if precond != "jacobi":
+                    side["pcg_achieved_gbs"] = (12.0 * nnz + 108.0 * n_unknowns) * ia["iterations"] / ia["solve_ms"] / 1e6
+                    jac_side = side
+                else:
+                    side.update(levels=ia["level_rows"], operator_complexity=ia["operator_complexity"])
+                    amg_side = side
+            except Exception as exc:      # the headline line must not depend on the side measurement
+                amg_side = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only), and the SAME sample through this
     # repo from the same csv file with the same call sequence (file -> netlist -> equivalent_resistance):
@@ -376,8 +390,8 @@ def run_ours(args):
         path = grid_csv(Ns)
         try:
             def gpu_from_csv():
-                net = cli.load_netlist_or_exit(path)          # what nodal-resistance FILE -s does
-                return float(n.equiv.equivalent_resistance(net, "1", "g", sparse=True))
+                netl = cli.load_netlist_or_exit(path)         # what nodal-resistance FILE -s does
+                return float(n.equiv.equivalent_resistance(netl, "1", "g", sparse=True))
             gpu_from_csv()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -392,22 +406,25 @@ def run_ours(args):
                 "host numbering / ingest included on both sides", "gpu_s": t_gpu, "cpu_s": dt, "cpu_kind": kind,
                 "speedup": dt / t_gpu, "R_gpu": r_gpu, "R_cpu": r_cpu, "R_rel_diff": abs(r_gpu - r_cpu) / abs(r_cpu)}
 
+    solver_name = {"amg": "aggregation-AMG preconditioned CG", "jacobi": "Jacobi-PCG"}[precond]
+    keys = ("assemble_wall_ms", "solve_wall_ms", "setup_ms", "solve_ms", "host_ms", "comm", "levels", "distributed_levels",
+            "level_rows", "replicated_rows", "kernels_per_iteration", "halo_recv", "restarts")
     line = {
         "metric": "unknowns_per_second", "value": value, "unit": "unknowns/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"grid2d_{N}x{N} equivalent resistance (config C5a): stamp + CSR build + "
-                               f"{'AMG' if args.precond == 'amg' and world == 1 else 'Jacobi'}-PCG rtol {RTOL}", "unknowns": n_unknowns, "components": ncomp,
-                   "nnz": nnz, "l2": "working set (>= 2.8 GB per CG iteration) is larger than the 126 MB L2",
+        "config": {"workload": f"grid2d_{N}x{N} equivalent resistance (config C5a): "
+                               f"{'select rank rows + ' if world > 1 else ''}stamp + CSR build + {solver_name} rtol {RTOL}",
+                   "unknowns": n_unknowns, "components": ncomp, "nnz": nnz, "precond": precond,
+                   "l2": "working set (>= 1.3 GB per level-0 sweep) is larger than the 126 MB L2",
                    "parallelism": f"rows x{world}" if world > 1 else "single GPU"},
         "time_to_solution_s": ms_per_step * 1e-3, "iterations": iters, "relres": info["relres"],
         "R": r, "R_minus_infinite_grid_limit": r - KNIGHT_LIMIT,
-        "pcg_solve_ms": solve_ms, "pcg_setup_ms": info.get("setup_ms"),
-        "dist_breakdown_ms": {k: info[k] for k in ("assemble_wall_ms", "solve_wall_ms", "host_ms", "comm") if k in info},
-        "pcg_achieved_gbs": pcg_bytes / (solve_ms * 1e-3) / 1e9 if world == 1 else None,
+        "step_breakdown": {k: info[k] for k in keys if k in info},
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
-        "cpu_baseline": cpu, "same_size_pair": same, "amg_pcg_opt_in": amg,
+        "cpu_baseline": cpu, "same_size_pair": same,
+        "jacobi_pcg_side": jac_side, "amg_pcg_side": amg_side,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -423,9 +440,11 @@ def main():
     ap.add_argument("--grid", type=int, default=4096, help="grid side (4096 -> 16.7M nodes, config C5a)")
     ap.add_argument("--ref-grid", type=int, default=400, help="grid side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precond", default="jacobi", choices=["jacobi", "amg"],
-                    help="single-GPU preconditioner of the timed step (multi-GPU runs use Jacobi)")
-    ap.add_argument("--no-amg", action="store_true", help="skip the side measurement of the AMG path")
+    ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"],
+                    help="preconditioner of the timed step on every GPU count (jacobi: the round-1 headline)")
+    ap.add_argument("--gather-below", type=int, default=0,
+                    help="AMG: levels with at most this many rows are replicated on every rank (0 = library default)")
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurement of the other preconditioner")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

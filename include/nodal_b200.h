@@ -225,6 +225,42 @@ int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, const int32_
                    double rtol, int32_t maxit,
                    int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
 
+/* Measurement aid for bench.py's roofline entry: average per-launch time (ms, CUDA events on
+ * `stream`, `reps` launches after two warm-up launches) of the level-0 SELL sweeps of the hierarchy:
+ * ms_out[0] q = A p with the p.q partial sums, [1] r = b - A x, [2] the damped-Jacobi sweep. */
+int nodal_amg_profile_sweeps(nodal_ctx* ctx, nodal_amg* h, int32_t reps, double* ms_out, void* stream);
+
+/* Row-partitioned assembly: a rank stamps the components that touch one of its rows [rb, re)
+ * (the loop of nodal/nodal.py:357-390 restricted to them, order kept, so the rank's rows of G are
+ * bit-identical to the single-GPU CSR).  _scan writes the exclusive scan of the selection flags to
+ * pos (device, ncomp entries) and the number selected to *count_h; _gather copies the selected rows
+ * of the eight columns, in order, into out_* (device, *count_h entries each).  R / A tables only
+ * (drv is copied, not renumbered). */
+int nodal_table_select_scan(nodal_ctx* ctx, int64_t ncomp, const int32_t* a, const int32_t* b,
+                            int32_t rb, int32_t re, uint32_t* pos, int64_t* count_h, void* stream);
+int nodal_table_select_gather(nodal_ctx* ctx, int64_t ncomp, const uint32_t* pos, int32_t rb, int32_t re,
+                              const uint8_t* type, const double* value, const int32_t* a, const int32_t* b,
+                              const int32_t* c, const int32_t* d, const int32_t* drv, const int32_t* branch,
+                              uint8_t* out_type, double* out_value, int32_t* out_a, int32_t* out_b,
+                              int32_t* out_c, int32_t* out_d, int32_t* out_drv, int32_t* out_branch,
+                              void* stream);
+
+/* Row-partitioned aggregation-AMG preconditioned CG (csrc/dist_amg.cu): same partition contract as
+ * nodal_dist_pcg, same call it replaces (spsolve, nodal/nodal.py:325, for R / A netlists).  Aggregates
+ * never cross the partition; levels with at most params[7] global rows (default 400 000) are gathered
+ * and handled by the single-GPU hierarchy replicated on every rank.  params (host, 8 doubles, 0 = default):
+ * passes, coarse, omega, scale, maxlevels, rounds, direct_max (as nodal_amg_create), gather_below.
+ * With one rank it is a graph-captured single-GPU form of nodal_amg_pcg.
+ * stats_h (32 doubles): [0] levels, [2] restarts, [3] solve ms, [4] setup ms, [5] coarsest rows,
+ * [7] coarsest solved directly, [8] distributed levels, [9] 2 = peer-memory exchanges / 0 = NCCL,
+ * [10] kernels per iteration, [11] rows of the first replicated level, [12] halo entries received per
+ * cycle, [16 + l] global rows of level l. */
+int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, const int32_t* bounds_h,
+                       int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* data,
+                       const double* rhs_local, double* x_local, const double* params,
+                       double rtol, int32_t maxit,
+                       int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

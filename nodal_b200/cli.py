@@ -13,8 +13,9 @@ def make_parser(description, file_help):
     parser.add_argument("netlist_path", metavar="FILE", help=file_help)
     parser.add_argument("-s", "--sparse", action="store_true", help="use a sparse matrix")
     # additions to the reference command line (both default to its behaviour)
-    parser.add_argument("--precond", choices=("jacobi", "amg"), default="jacobi",
-                        help="preconditioner of the sparse solve for resistor networks")
+    parser.add_argument("--precond", choices=("auto", "jacobi", "amg"), default="auto",
+                        help="preconditioner of the sparse solve for resistor networks (auto: aggregation "
+                             "AMG, Jacobi if that fails)")
     parser.add_argument("--check-connected", action="store_true",
                         help="with -s: fail on floating sub-circuits instead of printing what the "
                              "iterative solver returned")
@@ -24,7 +25,7 @@ def make_parser(description, file_help):
 def circuit_options(options):
     """Keyword arguments for Circuit from the parsed command line."""
     kw = {}
-    if options.sparse and options.precond != "jacobi":
+    if options.sparse and options.precond != "auto":
         kw["precond"] = options.precond
     if options.sparse and options.check_connected:
         kw["check_connected"] = True

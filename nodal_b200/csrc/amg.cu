@@ -22,234 +22,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "amg_core.cuh"
-#include "sparse.cuh"
-
-constexpr int AT = 256;
-
-// ------------------------------------------------------------------ setup kernels
-#define ROW_LOOP(i, n)                                                              \
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)(n); \
-         i += (int64_t)gridDim.x * blockDim.x)
-
-__global__ void __launch_bounds__(AT)
-amg_propose_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                   const double* __restrict__ data, const int32_t* __restrict__ match,
-                   int32_t* __restrict__ best) {
-    ROW_LOOP(i, n) best[i] = match[i] >= 0 ? -1 : amg_pick((int32_t)i, indptr, indices, data, match);
-}
-
-__global__ void __launch_bounds__(AT)
-amg_accept_kernel(int32_t n, const int32_t* __restrict__ best, int32_t* __restrict__ match) {
-    ROW_LOOP(i, n) {
-        if (match[i] >= 0) continue;
-        const int32_t b = best[i];
-        if (b >= 0 && best[b] == (int32_t)i) match[i] = b;
-    }
-}
-
-__global__ void __launch_bounds__(AT)
-amg_root_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                const double* __restrict__ data, const int32_t* __restrict__ match,
-                int32_t* __restrict__ root, u32* __restrict__ leader) {
-    ROW_LOOP(i, n) {
-        const int32_t r = amg_root((int32_t)i, indptr, indices, data, match);
-        root[i] = r;
-        leader[i] = r == (int32_t)i ? 1u : 0u;
-    }
-}
-
-__global__ void __launch_bounds__(AT)
-amg_assign_kernel(int32_t n, const int32_t* __restrict__ root, const u32* __restrict__ ids,
-                  int32_t* __restrict__ agg) {
-    ROW_LOOP(i, n) agg[i] = (int32_t)ids[root[i]];
-}
-
-__global__ void __launch_bounds__(AT)
-amg_compose_kernel(int32_t n, int32_t* __restrict__ comp, const int32_t* __restrict__ next) {
-    ROW_LOOP(i, n) comp[i] = next[comp[i]];
-}
-
-__global__ void __launch_bounds__(AT)
-amg_relabel_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                   const double* __restrict__ data, const int32_t* __restrict__ agg, int cb,
-                   u64* __restrict__ keys, double* __restrict__ vals) {
-    ROW_LOOP(i, n) {
-        const u64 hi = (u64)agg[i] << cb;
-        const int32_t e = indptr[i + 1];
-        for (int32_t p = indptr[i]; p < e; ++p) {
-            keys[p] = hi | (u64)agg[indices[p]];
-            vals[p] = data[p];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(AT)
-amg_pt_keys_kernel(int32_t n, const int32_t* __restrict__ agg, int cb, u64* __restrict__ keys,
-                   double* __restrict__ vals) {
-    ROW_LOOP(i, n) {
-        keys[i] = ((u64)agg[i] << cb) | (u64)i;
-        vals[i] = 1.0;
-    }
-}
-
-// ------------------------------------------------------------------ coarsest level: explicit inverse
-// [A | I] -> [I | A^-1] by Gauss-Jordan without pivoting (A is symmetric positive definite),
-// one launch per pivot, ping-pong between two n x 2n buffers so a step has no read/write race.
-__global__ void __launch_bounds__(AT)
-amg_dense_init_kernel(int32_t n, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                      const double* __restrict__ data, double* __restrict__ M) {
-    const int64_t W = 2 * (int64_t)n;
-    ROW_LOOP(i, n) {
-        M[i * W + n + i] = 1.0;
-        const int32_t e = indptr[i + 1];
-        for (int32_t p = indptr[i]; p < e; ++p) M[i * W + indices[p]] = data[p];
-    }
-}
-
-__global__ void __launch_bounds__(AT)
-amg_gj_step_kernel(int32_t n, int32_t k, const double* __restrict__ src, double* __restrict__ dst,
-                   int* __restrict__ bad) {
-    const int64_t W = 2 * (int64_t)n;
-    const double piv = src[k * W + k];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !(piv > 0.0) && *bad == 0) *bad = k + 1;
-    ROW_LOOP(idx, (int64_t)n * W) {
-        const int64_t i = idx / W, j = idx - i * W;
-        const double rkj = src[k * W + j] / piv;
-        dst[idx] = i == k ? rkj : src[idx] - src[i * W + k] * rkj;
-    }
-}
-
-__global__ void __launch_bounds__(AT)
-amg_dense_extract_kernel(int32_t n, const double* __restrict__ M, double* __restrict__ inv) {
-    const int64_t W = 2 * (int64_t)n;
-    ROW_LOOP(idx, (int64_t)n * n) {
-        const int64_t i = idx / n, j = idx - i * n;
-        inv[idx] = M[i * W + n + j];
-    }
-}
-
-// x = inv b, one warp per row
-__global__ void __launch_bounds__(AT)
-amg_gemv_kernel(int32_t n, const double* __restrict__ inv, const double* __restrict__ b,
-                double* __restrict__ x) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < n; r += nwarps) {
-        double acc = 0.0;
-        for (int32_t j = lane; j < n; j += 32) acc = fma(inv[r * n + j], b[j], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) x[r] = acc;
-    }
-}
-
-// ------------------------------------------------------------------ cycle kernels
-__global__ void __launch_bounds__(AT)
-amg_jacobi0_kernel(int32_t n, const double* __restrict__ dinv, const double* __restrict__ b,
-                   double omega, double* __restrict__ x) {
-    ROW_LOOP(i, n) x[i] = omega * dinv[i] * b[i];
-}
-
-// SELL-32 sweep, one warp per slice.
-//   MODE 0: y = A x, per-block partial sums of x.y        (CG: q = A p, p.q)
-//   MODE 1: y = b - A x                                   (residual)
-//   MODE 2: y = x + omega D^-1 (b - A x)                  (damped Jacobi sweep, out of place)
-template <int MODE>
-__global__ void __launch_bounds__(AT, 4)
-amg_sell_kernel(int32_t n, int32_t nslices, const u32* __restrict__ slice_w,
-                const int32_t* __restrict__ cols, const double* __restrict__ vals,
-                const double* __restrict__ dinv, const double* __restrict__ b,
-                const double* __restrict__ x, double omega, double* __restrict__ y,
-                double* __restrict__ part) {
-    __shared__ double red[33];
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    double dot = 0.0;
-    for (int64_t s = warp; s < nslices; s += nwarps) {
-        const u32 w0 = slice_w[s];
-        const int w = (int)(slice_w[s + 1] - w0);
-        const double acc = sell_row_dot(cols, vals, (int64_t)w0 * 32 + lane, w, x);
-        const int64_t r = s * 32 + lane;
-        if (r < n) {
-            if (MODE == 0) { y[r] = acc; dot = fma(x[r], acc, dot); }
-            if (MODE == 1) y[r] = b[r] - acc;
-            if (MODE == 2) y[r] = x[r] + omega * dinv[r] * (b[r] - acc);
-        }
-    }
-    if (MODE == 0) {
-        const double t = block_sum(dot, red);
-        if (threadIdx.x == 0) part[blockIdx.x] = t;
-    }
-}
-
-// bc[I] = sum of r over the members of aggregate I, in increasing row order
-__global__ void __launch_bounds__(AT)
-amg_restrict_kernel(int32_t nc, const int32_t* __restrict__ pt_ptr, const int32_t* __restrict__ pt_idx,
-                    const double* __restrict__ r, double* __restrict__ bc) {
-    ROW_LOOP(I, nc) {
-        double s = 0.0;
-        const int32_t e = pt_ptr[I + 1];
-        for (int32_t p = pt_ptr[I]; p < e; ++p) s += r[pt_idx[p]];
-        bc[I] = s;
-    }
-}
-
-__global__ void __launch_bounds__(AT)
-amg_prolong_kernel(int32_t n, const int32_t* __restrict__ agg, const double* __restrict__ xc,
-                   double scale, const double* __restrict__ x, double* __restrict__ xa) {
-    ROW_LOOP(i, n) xa[i] = x[i] + scale * xc[agg[i]];
-}
-
-// ------------------------------------------------------------------ CG vector kernels
-__global__ void __launch_bounds__(AT)
-apcg_dot_kernel(int32_t n, const double* __restrict__ a, const double* __restrict__ b,
-                double* __restrict__ part) {
-    __shared__ double red[33];
-    double t = 0.0;
-    ROW_LOOP(i, n) t = fma(a[i], b[i], t);
-    t = block_sum(t, red);
-    if (threadIdx.x == 0) part[blockIdx.x] = t;
-}
-
-__global__ void __launch_bounds__(AT)
-apcg_sum_kernel(const double* __restrict__ part, int count, double* __restrict__ out) {
-    __shared__ double red[33];
-    const double t = reduce_partials(part, count, red);
-    if (threadIdx.x == 0) out[0] = t;
-}
-
-// alpha = rz / p.q ; x += alpha p ; r -= alpha q ; partial sums of r.r
-__global__ void __launch_bounds__(AT)
-apcg_update_kernel(int32_t n, const double* __restrict__ part_pq, int npq, const double* __restrict__ rz,
-                   const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
-                   double* __restrict__ r, double* __restrict__ part_rr) {
-    __shared__ double red[33];
-    const double pq = reduce_partials(part_pq, npq, red);
-    const double alpha = rz[0] / pq;
-    double t = 0.0;
-    ROW_LOOP(i, n) {
-        x[i] = fma(alpha, p[i], x[i]);
-        const double ri = fma(-alpha, q[i], r[i]);
-        r[i] = ri;
-        t = fma(ri, ri, t);
-    }
-    t = block_sum(t, red);
-    if (threadIdx.x == 0) part_rr[blockIdx.x] = t;
-}
-
-// rz' = r.z (from partials) ; beta = rz'/rz ; p = z + beta p
-__global__ void __launch_bounds__(AT)
-apcg_direction_kernel(int32_t n, const double* __restrict__ part_rz, int nrz,
-                      const double* __restrict__ rz_old, double* __restrict__ rz_new,
-                      const double* __restrict__ z, double* __restrict__ p, int first) {
-    __shared__ double red[33];
-    const double rzn = reduce_partials(part_rz, nrz, red);
-    const double beta = first ? 0.0 : rzn / rz_old[0];
-    ROW_LOOP(i, n) p[i] = first ? z[i] : fma(beta, p[i], z[i]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) rz_new[0] = rzn;
-}
+#include "amg_host.cuh"
 
 // ------------------------------------------------------------------ host side
 struct AmgLevel {
@@ -280,81 +53,31 @@ struct nodal_amg {
     float setup_ms = 0.f;
 };
 
-namespace {
-
-int rows_grid(const nodal_ctx* ctx, int64_t work) {
-    int64_t b = (work + AT - 1) / AT;
-    const int64_t cap = (int64_t)ctx->num_sms * 16;
-    if (b < 1) b = 1;
-    return (int)(b < cap ? b : cap);
-}
-int sell_grid(const nodal_ctx* ctx, int32_t nslices) {
-    int64_t b = ((int64_t)nslices * 32 + AT - 1) / AT;
-    const int64_t cap = (int64_t)ctx->num_sms * 4;
-    if (b < 1) b = 1;
-    return (int)(b < cap ? b : cap);
-}
-int bit_length(int64_t v) {
-    int b = 1;
-    while ((v >> b) != 0) ++b;
-    return b;
-}
-
-template <typename T>
-T* pool(nodal_ctx* ctx, size_t count) {
-    T* p = static_cast<T*>(ctx_pool_alloc(ctx, sizeof(T) * (count ? count : 1)));
-    if (!p) nodal_set_error("amg: out of device memory (%zu bytes)", sizeof(T) * count);
-    return p;
-}
-
-// A pool allocation that goes back to the pool when the scope ends, unless keep() hands it on.
-// (Frees are stream ordered: every user of these buffers runs on the one setup stream.)
-template <typename T>
-struct Scratch {
-    nodal_ctx* ctx;
-    T* ptr;
-    Scratch(nodal_ctx* c, size_t count) : ctx(c), ptr(pool<T>(c, count)) {}
-    ~Scratch() { ctx_pool_free(ctx, ptr); }
-    Scratch(const Scratch&) = delete;
-    Scratch& operator=(const Scratch&) = delete;
-    T* keep() { T* p = ptr; ptr = nullptr; return p; }
-    operator T*() const { return ptr; }
-};
-
-struct Csr {
-    int32_t n = 0;
-    int64_t nnz = 0;
-    const int32_t* indptr = nullptr;
-    const int32_t* indices = nullptr;
-    const double* data = nullptr;
-    bool owned = false;
-};
-void free_csr(nodal_ctx* ctx, Csr& a) {
+void amg_free_csr(nodal_ctx* ctx, AmgCsr& a) {
     if (a.owned) {
         ctx_pool_free(ctx, const_cast<int32_t*>(a.indptr));
         ctx_pool_free(ctx, const_cast<int32_t*>(a.indices));
         ctx_pool_free(ctx, const_cast<double*>(a.data));
     }
-    a = Csr();
+    a = AmgCsr();
 }
 
-// One pairwise pass: agg_out[n] (pool, owned by the caller) and the number of aggregates.
-int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cudaStream_t st) {
-    nodal_ctx* ctx = h->ctx;
+int amg_aggregate(nodal_ctx* ctx, int rounds, const AmgCsr& A, int32_t nown, int32_t base,
+                  int32_t** agg_out, int32_t* nc_out, cudaStream_t st) {
     const int32_t n = A.n;
-    Scratch<int32_t> match(ctx, n), best(ctx, n);
-    Scratch<u32> leader(ctx, n);
+    AmgScratch<int32_t> match(ctx, n), best(ctx, n);
+    AmgScratch<u32> leader(ctx, n);
     if (!match.ptr || !best.ptr || !leader.ptr) return NODAL_CUDA_ERROR;
-    const int grid = rows_grid(ctx, n);
+    const int grid = amg_rows_grid(ctx, n);
     CUDA_TRY(cudaMemsetAsync(match, 0xFF, sizeof(int32_t) * (size_t)n, st));
-    for (int r = 0; r < h->rounds; ++r) {
-        amg_propose_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, best);
+    for (int r = 0; r < rounds; ++r) {
+        amg_propose_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, best, nown, base);
         KERNEL_CHECK();
         amg_accept_kernel<<<grid, AT, 0, st>>>(n, best, match);
         KERNEL_CHECK();
     }
     int32_t* root = best;       // the proposals are not needed any more
-    amg_root_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, root, leader);
+    amg_root_kernel<<<grid, AT, 0, st>>>(n, A.indptr, A.indices, A.data, match, root, leader, nown, base);
     KERNEL_CHECK();
     NODAL_TRY(ctx_reserve(ctx, scan_scratch_bytes(n) + 4096));
     u32* total = carve<u32>(ctx, 16);
@@ -369,6 +92,43 @@ int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cu
     *nc_out = (int32_t)total_h[0];
     *agg_out = match.keep();
     return NODAL_OK;
+}
+
+int amg_transpose_pattern(nodal_ctx* ctx, int32_t n, const int32_t* agg, int32_t** pt_ptr_out,
+                          int32_t** pt_idx_out, cudaStream_t st) {
+    AmgScratch<u64> keys(ctx, n);
+    AmgScratch<double> vals(ctx, n), rhs(ctx, (size_t)n + 1), ones(ctx, n);
+    if (!keys.ptr || !vals.ptr || !rhs.ptr || !ones.ptr) return NODAL_CUDA_ERROR;
+    const int cb = amg_bit_length(n);
+    amg_pt_keys_kernel<<<amg_rows_grid(ctx, n), AT, 0, st>>>(n, agg, cb, keys, vals);
+    KERNEL_CHECK();
+    int64_t cnt = 0;
+    NODAL_TRY(nodal_csr_build(ctx, n, n, cb, reinterpret_cast<uint64_t*>(keys.ptr), vals, rhs, &cnt, st));
+    if (cnt != n) {
+        nodal_set_error("amg: internal error, P^T has %lld entries for %d rows", (long long)cnt, n);
+        return NODAL_CUDA_ERROR;
+    }
+    AmgScratch<int32_t> pp(ctx, (size_t)n + 1), pi(ctx, n);
+    if (!pp.ptr || !pi.ptr) return NODAL_CUDA_ERROR;
+    NODAL_TRY(nodal_csr_fetch(ctx, n, n, pp, pi, ones, st));
+    *pt_ptr_out = pp.keep();
+    *pt_idx_out = pi.keep();
+    return NODAL_OK;
+}
+
+namespace {
+
+int rows_grid(const nodal_ctx* ctx, int64_t work) { return amg_rows_grid(ctx, work); }
+int sell_grid(const nodal_ctx* ctx, int32_t nslices) { return amg_sell_grid(ctx, nslices); }
+int bit_length(int64_t v) { return amg_bit_length(v); }
+template <typename T>
+T* pool(nodal_ctx* ctx, size_t count) { return amg_pool<T>(ctx, count); }
+template <typename T>
+using Scratch = AmgScratch<T>;
+using Csr = AmgCsr;
+void free_csr(nodal_ctx* ctx, Csr& a) { amg_free_csr(ctx, a); }
+int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cudaStream_t st) {
+    return amg_aggregate(h->ctx, h->rounds, A, 0x7fffffff, 0, agg_out, nc_out, st);
 }
 
 // Ac = P^T A P for the piecewise-constant P of `agg`.
@@ -397,27 +157,8 @@ int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* ou
     return NODAL_OK;
 }
 
-// Members of every aggregate (CSR pattern of P^T), rows in increasing order.
 int transpose_pattern(nodal_amg* h, AmgLevel& L, cudaStream_t st) {
-    nodal_ctx* ctx = h->ctx;
-    const int32_t n = L.n;
-    Scratch<u64> keys(ctx, n);
-    Scratch<double> vals(ctx, n), rhs(ctx, (size_t)n + 1), ones(ctx, n);
-    if (!keys.ptr || !vals.ptr || !rhs.ptr || !ones.ptr) return NODAL_CUDA_ERROR;
-    const int cb = bit_length(n);
-    amg_pt_keys_kernel<<<rows_grid(ctx, n), AT, 0, st>>>(n, L.agg, cb, keys, vals);
-    KERNEL_CHECK();
-    int64_t cnt = 0;
-    NODAL_TRY(nodal_csr_build(ctx, n, n, cb, reinterpret_cast<uint64_t*>(keys.ptr), vals, rhs, &cnt, st));
-    if (cnt != n) {
-        nodal_set_error("amg: internal error, P^T has %lld entries for %d rows", (long long)cnt, n);
-        return NODAL_CUDA_ERROR;
-    }
-    L.pt_ptr = pool<int32_t>(ctx, (size_t)n + 1);      // owned by the level from here on
-    L.pt_idx = pool<int32_t>(ctx, n);
-    if (!L.pt_ptr || !L.pt_idx) return NODAL_CUDA_ERROR;
-    NODAL_TRY(nodal_csr_fetch(ctx, n, n, L.pt_ptr, L.pt_idx, ones, st));
-    return NODAL_OK;
+    return amg_transpose_pattern(h->ctx, L.n, L.agg, &L.pt_ptr, &L.pt_idx, st);
 }
 
 int invert_coarsest(nodal_amg* h, const AmgLevel& L, cudaStream_t st) {
@@ -799,5 +540,37 @@ extern "C" int nodal_amg_pcg(nodal_ctx* ctx, nodal_amg* h, const double* rhs, do
         stats_h[6] = n ? rows / n : 0.0;                       // grid complexity
         stats_h[7] = h->inv ? 1.0 : 0.0;
     }
+    return rc;
+}
+
+// Per-launch time of the level-0 SELL sweeps (the dominant kernels of the AMG-PCG step) for the
+// roofline entry of bench.py: `reps` launches of each mode on the hierarchy's own level-0
+// operator and work vectors, bracketed by CUDA events on `stream`.
+// ms_out[0] = MODE 0 (q = A p + dot), [1] = MODE 1 (residual), [2] = MODE 2 (Jacobi sweep).
+extern "C" int nodal_amg_profile_sweeps(nodal_ctx* ctx, nodal_amg* h, int32_t reps, double* ms_out, void* stream) {
+    if (!ctx || !h || h->ctx != ctx || !ms_out || reps < 1 || h->lv.empty()) return NODAL_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const AmgLevel& A = h->lv[0];
+    CUDA_TRY(cudaMemsetAsync(h->p, 0, sizeof(double) * (size_t)A.n, st));
+    CUDA_TRY(cudaMemsetAsync(h->r, 0, sizeof(double) * (size_t)A.n, st));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int rc = NODAL_OK;
+    for (int mode = 0; mode < 3 && rc == NODAL_OK; ++mode) {
+        for (int k = -2; k < reps && rc == NODAL_OK; ++k) {      // two warm-up launches
+            if (k == 0) cudaEventRecord(e0, st);
+            if (mode == 0) rc = sell_sweep<0>(h, A, nullptr, h->p, h->q, h->part, st);
+            if (mode == 1) rc = sell_sweep<1>(h, A, h->r, h->p, h->q, nullptr, st);
+            if (mode == 2) rc = sell_sweep<2>(h, A, h->r, h->p, h->q, nullptr, st);
+        }
+        cudaEventRecord(e1, st);
+        float ms = 0.f;
+        if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+        ms_out[mode] = ms / reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return rc;
 }

@@ -27,8 +27,13 @@ AMG_HD uint32_t amg_edge_hash(int32_t i, int32_t j) {
 
 // The neighbour row i prefers: the largest coupling -a_ij > 0, then the largest edge hash, then
 // the smallest index.  With `match` only neighbours that are still unmatched qualify.
+// Row-partitioned setup (dist_amg.cu): rows and columns are LOCAL indices, columns >= nown are
+// halo entries owned by another rank and never qualify (aggregates do not cross the partition),
+// and `base` (the global index of local row 0) keeps the tie-breaking hash a function of the
+// global edge, so the aggregates do not depend on how many ranks there are beyond that rule.
 AMG_HD int32_t amg_pick(int32_t i, const int32_t* indptr, const int32_t* indices,
-                        const double* data, const int32_t* match) {
+                        const double* data, const int32_t* match,
+                        int32_t nown = 0x7fffffff, int32_t base = 0) {
     int32_t best = -1;
     double bw = 0.0;
     uint32_t bh = 0u;
@@ -36,10 +41,10 @@ AMG_HD int32_t amg_pick(int32_t i, const int32_t* indptr, const int32_t* indices
     for (int32_t p = indptr[i]; p < e; ++p) {
         const int32_t j = indices[p];
         const double a = data[p];
-        if (j == i || !(a < 0.0)) continue;
+        if (j == i || j >= nown || !(a < 0.0)) continue;
         if (match && match[j] >= 0) continue;
         const double w = -a;
-        const uint32_t h = amg_edge_hash(i, j);
+        const uint32_t h = amg_edge_hash(i + base, j + base);
         if (best < 0 || w > bw || (w == bw && (h > bh || (h == bh && j < best)))) {
             best = j;
             bw = w;
@@ -53,10 +58,11 @@ AMG_HD int32_t amg_pick(int32_t i, const int32_t* indptr, const int32_t* indices
 // alone joins the pair of its preferred neighbour if that neighbour is matched (it never chains
 // onto another lone row), otherwise it stays a singleton.
 AMG_HD int32_t amg_root(int32_t i, const int32_t* indptr, const int32_t* indices,
-                        const double* data, const int32_t* match) {
+                        const double* data, const int32_t* match,
+                        int32_t nown = 0x7fffffff, int32_t base = 0) {
     const int32_t m = match[i];
     if (m >= 0) return m < i ? m : i;
-    const int32_t t = amg_pick(i, indptr, indices, data, nullptr);
+    const int32_t t = amg_pick(i, indptr, indices, data, nullptr, nown, base);
     if (t >= 0) {
         const int32_t mt = match[t];
         if (mt >= 0) return mt < t ? mt : t;

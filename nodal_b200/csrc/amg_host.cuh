@@ -1,0 +1,64 @@
+// Host-side building blocks of the AMG setup shared by amg.cu (single GPU) and dist_amg.cu
+// (row-partitioned): pool-backed scratch buffers, launch grids, one pairwise aggregation pass
+// and the transposed prolongation pattern.
+#pragma once
+#include "amg_kernels.cuh"
+
+static inline int amg_rows_grid(const nodal_ctx* ctx, int64_t work) {
+    int64_t b = (work + AT - 1) / AT;
+    const int64_t cap = (int64_t)ctx->num_sms * 16;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+static inline int amg_sell_grid(const nodal_ctx* ctx, int32_t nslices) {
+    int64_t b = ((int64_t)nslices * 32 + AT - 1) / AT;
+    const int64_t cap = (int64_t)ctx->num_sms * 4;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+static inline int amg_bit_length(int64_t v) {
+    int b = 1;
+    while ((v >> b) != 0) ++b;
+    return b;
+}
+
+template <typename T>
+static inline T* amg_pool(nodal_ctx* ctx, size_t count) {
+    T* p = static_cast<T*>(ctx_pool_alloc(ctx, sizeof(T) * (count ? count : 1)));
+    if (!p) nodal_set_error("amg: out of device memory (%zu bytes)", sizeof(T) * count);
+    return p;
+}
+
+// A pool allocation that goes back to the pool when the scope ends, unless keep() hands it on.
+// (Frees are stream ordered: every user of these buffers runs on the one setup stream.)
+template <typename T>
+struct AmgScratch {
+    nodal_ctx* ctx;
+    T* ptr;
+    AmgScratch(nodal_ctx* c, size_t count) : ctx(c), ptr(amg_pool<T>(c, count)) {}
+    ~AmgScratch() { ctx_pool_free(ctx, ptr); }
+    AmgScratch(const AmgScratch&) = delete;
+    AmgScratch& operator=(const AmgScratch&) = delete;
+    T* keep() { T* p = ptr; ptr = nullptr; return p; }
+    operator T*() const { return ptr; }
+};
+
+struct AmgCsr {
+    int32_t n = 0;
+    int64_t nnz = 0;
+    const int32_t* indptr = nullptr;
+    const int32_t* indices = nullptr;
+    const double* data = nullptr;
+    bool owned = false;
+};
+void amg_free_csr(nodal_ctx* ctx, AmgCsr& a);
+
+// One pairwise pass over the rows of A: *agg_out[n] (pool, owned by the caller) and the number
+// of aggregates.  Columns >= nown never qualify and `base` offsets the tie-breaking hash
+// (amg_core.cuh); the single-GPU setup passes nown = INT32_MAX, base = 0.
+int amg_aggregate(nodal_ctx* ctx, int rounds, const AmgCsr& A, int32_t nown, int32_t base,
+                  int32_t** agg_out, int32_t* nc_out, cudaStream_t st);
+// Members of every aggregate (CSR pattern of P^T), rows in increasing order; pool buffers
+// pt_ptr[n + 1] / pt_idx[n] owned by the caller.
+int amg_transpose_pattern(nodal_ctx* ctx, int32_t n, const int32_t* agg, int32_t** pt_ptr,
+                          int32_t** pt_idx, cudaStream_t st);

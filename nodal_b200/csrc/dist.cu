@@ -17,29 +17,13 @@
 // The scalar results are bitwise identical on all ranks, so every rank takes the same
 // convergence decision with no extra traffic.  libnccl.so.2 is dlopen'ed: the single-GPU
 // library has no NCCL dependency.
-#include <dlfcn.h>
-#include <nccl.h>
-
 #include <algorithm>
 #include <chrono>
 #include <vector>
 
+#include "dist_common.cuh"
 #include "pcg_kernels.cuh"
 
-namespace {
-struct NcclApi {
-    void* handle = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
 NcclApi g_nccl;
 
 int load_nccl() {
@@ -61,6 +45,7 @@ int load_nccl() {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
     SYM(AllGather, "ncclAllGather")
+    SYM(Broadcast, "ncclBroadcast")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
@@ -70,22 +55,8 @@ int load_nccl() {
     g_nccl.handle = h;
     return NODAL_OK;
 }
-}  // namespace
 
-#define NCCL_TRY(expr)                                                                       \
-    do {                                                                                     \
-        ncclResult_t _r = (expr);                                                            \
-        if (_r != ncclSuccess) {                                                             \
-            nodal_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                    \
-                            g_nccl.GetErrorString(_r));                                      \
-            return NODAL_CUDA_ERROR;                                                         \
-        }                                                                                    \
-    } while (0)
-
-// Symmetric peer-mapped buffer (one per rank, same size everywhere): a 4 KB mailbox followed
-// by the rank's u vector [owned | halo].  Peers write halo entries and reduction operands
-// straight into it over NVLink (CUDA IPC mappings), so the iteration needs no NCCL call.
-constexpr int P2P_MAXR = 8;
+// The PCG's peer-mapped buffer: a 4 KB mailbox followed by the rank's u vector [owned | halo].
 constexpr size_t P2P_HDR = 4096;
 struct P2PMail {
     double red[2][P2P_MAXR][4];            // [parity][source rank] = {gamma, delta, rr, tag}
@@ -93,26 +64,14 @@ struct P2PMail {
     unsigned long long err;
 };
 
-struct nodal_dist {
-    ncclComm_t comm = nullptr;
-    int rank = 0, nranks = 1, device = 0;
-    // peer-memory path
-    bool p2p_disabled = false;
-    char* shm = nullptr;
-    size_t shm_bytes = 0;
-    std::vector<char*> peer;               // host copy of the mapped base pointers (peer[rank] = shm)
-    char** peer_dev = nullptr;             // the same on the device
-    unsigned long long* seq = nullptr;     // device: reductions completed since the buffer was made
-};
-
-static void p2p_release(nodal_dist* d) {
-    for (size_t o = 0; o < d->peer.size(); ++o)
-        if ((int)o != d->rank && d->peer[o]) cudaIpcCloseMemHandle(d->peer[o]);
-    d->peer.clear();
-    if (d->shm) cudaFree(d->shm);
-    if (d->peer_dev) cudaFree(d->peer_dev);
-    if (d->seq) cudaFree(d->seq);
-    d->shm = nullptr; d->peer_dev = nullptr; d->seq = nullptr; d->shm_bytes = 0;
+void peer_heap_release(nodal_dist* d, PeerHeap* h) {
+    for (size_t o = 0; o < h->peer.size(); ++o)
+        if ((int)o != d->rank && h->peer[o]) cudaIpcCloseMemHandle(h->peer[o]);
+    h->peer.clear();
+    if (h->shm) cudaFree(h->shm);
+    if (h->peer_dev) cudaFree(h->peer_dev);
+    if (h->seq) cudaFree(h->seq);
+    h->shm = nullptr; h->peer_dev = nullptr; h->seq = nullptr; h->bytes = 0;
 }
 
 extern "C" int nodal_dist_unique_id(uint8_t* id_h) {
@@ -149,7 +108,8 @@ extern "C" int nodal_dist_destroy(nodal_dist* d) {
     if (!d) return NODAL_OK;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
-    p2p_release(d);
+    peer_heap_release(d, &d->pcg);
+    peer_heap_release(d, &d->amg);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     delete d;
     return NODAL_OK;
@@ -376,16 +336,6 @@ __global__ void cgcg_scalars_kernel(PcgDev* dev, double* SC, double rtol, int ma
 }
 
 // ---------------------------------------------------------------- peer-memory kernels
-__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-constexpr long long P2P_SPIN_LIMIT = 6000000000ll;   // ~3 s of SM clocks, then give up (no hang)
-
 // One CTA: copy the entries every peer needs from my u into the halo tail of THEIR u, then
 // raise my flag in their mailbox.
 __global__ void __launch_bounds__(1024)
@@ -796,25 +746,24 @@ static int grid_of(nodal_ctx* ctx, int64_t work) {
     return (int)std::max<int64_t>(1, std::min(b, cap));
 }
 
-// Collective: make sure every rank owns a peer-mapped buffer of at least `bytes`.
-// Returns NODAL_OK and sets *usable; any failure on any rank disables the path everywhere.
-static int p2p_ensure(nodal_ctx* ctx, nodal_dist* d, size_t bytes, cudaStream_t st, bool* usable) {
+int peer_heap_ensure(nodal_ctx* ctx, nodal_dist* d, PeerHeap* hp, size_t bytes, size_t zero_bytes,
+                     cudaStream_t st, bool* usable) {
     *usable = false;
     const int R = d->nranks, me = d->rank;
     if (R < 2 || R > P2P_MAXR || d->p2p_disabled || getenv("NODAL_DIST_NO_P2P")) return NODAL_OK;
     int* flag_dev = nullptr;
     CUDA_TRY(cudaMalloc(&flag_dev, 256));
     int ok = 1;
-    if (d->shm_bytes < bytes) {
+    if (hp->bytes < bytes) {
         CUDA_TRY(cudaStreamSynchronize(st));
-        p2p_release(d);
+        peer_heap_release(d, hp);
         const size_t want = align_up(bytes + bytes / 4, 2 << 20);
         cudaIpcMemHandle_t mine;
         char* handles_dev = nullptr;
         std::vector<cudaIpcMemHandle_t> all((size_t)R);
-        if (cudaMalloc(&d->shm, want) != cudaSuccess) ok = 0;
-        if (ok && cudaMemset(d->shm, 0, P2P_HDR) != cudaSuccess) ok = 0;
-        if (ok && cudaIpcGetMemHandle(&mine, d->shm) != cudaSuccess) ok = 0;
+        if (cudaMalloc(&hp->shm, want) != cudaSuccess) ok = 0;
+        if (ok && cudaMemset(hp->shm, 0, std::min(zero_bytes, want)) != cudaSuccess) ok = 0;
+        if (ok && cudaIpcGetMemHandle(&mine, hp->shm) != cudaSuccess) ok = 0;
         if (!ok) memset(&mine, 0, sizeof(mine));
         (void)cudaGetLastError();
         CUDA_TRY(cudaMalloc(&handles_dev, sizeof(cudaIpcMemHandle_t) * (size_t)(R + 1)));
@@ -824,23 +773,23 @@ static int p2p_ensure(nodal_ctx* ctx, nodal_dist* d, size_t bytes, cudaStream_t 
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaMemcpy(all.data(), handles_dev, sizeof(cudaIpcMemHandle_t) * (size_t)R, cudaMemcpyDeviceToHost));
         cudaFree(handles_dev);
-        d->peer.assign((size_t)R, nullptr);
+        hp->peer.assign((size_t)R, nullptr);
         for (int o = 0; o < R && ok; ++o) {
-            if (o == me) { d->peer[o] = d->shm; continue; }
+            if (o == me) { hp->peer[o] = hp->shm; continue; }
             void* ptr = nullptr;
             if (cudaIpcOpenMemHandle(&ptr, all[o], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 ok = 0;
                 (void)cudaGetLastError();
             }
-            d->peer[o] = static_cast<char*>(ptr);
+            hp->peer[o] = static_cast<char*>(ptr);
         }
         if (ok) {
-            if (cudaMalloc(&d->peer_dev, sizeof(char*) * P2P_MAXR) != cudaSuccess ||
-                cudaMemcpy(d->peer_dev, d->peer.data(), sizeof(char*) * (size_t)R, cudaMemcpyHostToDevice) != cudaSuccess ||
-                cudaMalloc(&d->seq, 256) != cudaSuccess || cudaMemset(d->seq, 0, 256) != cudaSuccess)
+            if (cudaMalloc(&hp->peer_dev, sizeof(char*) * P2P_MAXR) != cudaSuccess ||
+                cudaMemcpy(hp->peer_dev, hp->peer.data(), sizeof(char*) * (size_t)R, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMalloc(&hp->seq, 256) != cudaSuccess || cudaMemset(hp->seq, 0, 256) != cudaSuccess)
                 ok = 0;
         }
-        if (ok) d->shm_bytes = want;
+        if (ok) hp->bytes = want;
     }
     // agree on the outcome (also a barrier: nobody writes a mailbox before it has been zeroed)
     CUDA_TRY(cudaMemcpy(flag_dev, &ok, sizeof(int), cudaMemcpyHostToDevice));
@@ -850,7 +799,7 @@ static int p2p_ensure(nodal_ctx* ctx, nodal_dist* d, size_t bytes, cudaStream_t 
     CUDA_TRY(cudaMemcpy(&all_ok, flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(flag_dev);
     if (!all_ok) {
-        p2p_release(d);
+        peer_heap_release(d, hp);
         d->p2p_disabled = true;
         return NODAL_OK;
     }
@@ -1012,7 +961,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         }
         // ---------------- peer-memory path: symmetric buffer + push metadata ----------------
         bool p2p = false;
-        NODAL_TRY(p2p_ensure(ctx, d, P2P_HDR + (size_t)max_units * 256 * sizeof(double), st, &p2p));
+        NODAL_TRY(peer_heap_ensure(ctx, d, &d->pcg, P2P_HDR + (size_t)max_units * 256 * sizeof(double), P2P_HDR, st, &p2p));
         int32_t* send_off_dev = nullptr;
         int32_t* need_cnt_dev = nullptr;
         long long* dest_off_dev = nullptr;
@@ -1143,7 +1092,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         NODAL_TRY(ctx_reserve(ctx, 7 * vloc + 2 * vext + 8 * align_up(sizeof(double) * gmax, 256) + 8192));
         // the vector the SpMV gathers from lives in the layout [owned | halo] (in the peer-mapped
         // buffer on the p2p path): u = D^-1 r in general, r itself when the diagonal is 1
-        double* ext = p2p ? reinterpret_cast<double*>(d->shm + P2P_HDR)
+        double* ext = p2p ? reinterpret_cast<double*>(d->pcg.shm + P2P_HDR)
                           : carve<double>(ctx, (size_t)nloc + nhalo + 2);
         double* r = unit ? ext : carve<double>(ctx, nloc);
         double* u = ext;
@@ -1210,18 +1159,18 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
                 // two kernels, no NCCL: push + halo wait inside the vector pass, all-reduce inside the SpMV
                 if (unit)
                     dist_vector_push_kernel<true><<<g2, PCG_THREADS, 0, sx>>>(
-                        dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
+                        dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->pcg.seq, R, me,
                         send_idx, send_off_dev, dest_off_dev, need_cnt_dev, blist_dev, nb_rows, nbc, push_rng_dev,
-                        bmask_dev, d->peer_dev);
+                        bmask_dev, d->pcg.peer_dev);
                 else
                     dist_vector_push_kernel<false><<<g2, PCG_THREADS, 0, sx>>>(
-                        dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->seq, R, me,
+                        dev, nloc, cur, nxt, x_local, r, p, s, w, dinv, u, part_g, part_rr, sy, d->pcg.seq, R, me,
                         send_idx, send_off_dev, dest_off_dev, need_cnt_dev, blist_dev, nb_rows, nbc, push_rng_dev,
-                        bmask_dev, d->peer_dev);
+                        bmask_dev, d->pcg.peer_dev);
                 KERNEL_CHECK();
                 dist_spmv_allreduce_sell_kernel<<<A.g1, PCG_THREADS, 0, sx>>>(
                     dev, nloc, sell->nslices, sell->slice_w, sell->cols, sell->vals, ext, w, part_d, part_g,
-                    part_rr, g2, sy, d->seq, R, me, d->peer_dev, nxt);
+                    part_rr, g2, sy, d->pcg.seq, R, me, d->pcg.peer_dev, nxt);
                 KERNEL_CHECK();
                 return NODAL_OK;
             }
@@ -1233,19 +1182,19 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
                                                                      part_g, part_rr);
             KERNEL_CHECK();
             if (p2p) {
-                p2p_push_kernel<<<1, 1024, 0, sx>>>(dev, d->seq, R, me, send_idx, send_off_dev, dest_off_dev,
-                                                    d->peer_dev, ext);
+                p2p_push_kernel<<<1, 1024, 0, sx>>>(dev, d->pcg.seq, R, me, send_idx, send_off_dev, dest_off_dev,
+                                                    d->pcg.peer_dev, ext);
                 KERNEL_CHECK();
-                p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->seq, R, me, need_cnt_dev,
-                                                       reinterpret_cast<P2PMail*>(d->shm));
+                p2p_wait_halo_kernel<<<1, 32, 0, sx>>>(dev, d->pcg.seq, R, me, need_cnt_dev,
+                                                       reinterpret_cast<P2PMail*>(d->pcg.shm));
                 KERNEL_CHECK();
             } else {
                 NODAL_TRY(exchange(ext, sx));
             }
             NODAL_TRY(launch_k1(A, dev, ext, w, part_d, sx));
             if (p2p) {
-                p2p_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, d->seq, R, me, part_g, part_rr, g2, part_d, A.g1,
-                                                            d->peer_dev, nxt);
+                p2p_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, d->pcg.seq, R, me, part_g, part_rr, g2, part_d, A.g1,
+                                                            d->pcg.peer_dev, nxt);
                 KERNEL_CHECK();
             } else {
                 cgcg_reduce_kernel<<<1, PCG_THREADS, 0, sx>>>(dev, part_g, part_rr, nullptr, g2, part_d, A.g1, nxt, 0);

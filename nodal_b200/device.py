@@ -126,6 +126,13 @@ class DeviceAMG:
                    "nodal_amg_apply")
         return z
 
+    def profile_sweeps(self, reps=64):
+        """Average ms per launch of the level-0 SELL sweeps: dict(spmv_dot, residual, jacobi)."""
+        ms = (C.c_double * 4)()
+        _lib.check(self.dev.lib.nodal_amg_profile_sweeps(self.dev.ctx, self.handle, int(reps), ms, self.dev.stream()),
+                   "nodal_amg_profile_sweeps")
+        return dict(spmv_dot=ms[0], residual=ms[1], jacobi=ms[2])
+
     def solve(self, rhs, rtol=1e-10, maxit=None, x0=None):
         dev, n = self.dev, self.csr.n
         x = dev.zeros(max(2, n), dev.torch.float64)[:n] if x0 is None else x0.clone()
@@ -214,12 +221,14 @@ class Device:
 
     def assemble_csr(self, table: ComponentTable, dtab=None):
         """Stamp + CSR build.  Returns (DeviceCSR, rhs tensor)."""
-        torch = self.torch
-        n, ncomp = table.n, len(table)
-        stride = coo_stride(table)
         if dtab is None:
             dtab = self.upload_table(table)
-        keys, vals, cb = self.stamp_coo(dtab, ncomp, table.kcl, n, stride)
+        return self.assemble_csr_raw(dtab, len(table), table.kcl, table.n, coo_stride(table))
+
+    def assemble_csr_raw(self, dtab, ncomp, kcl, n, stride):
+        """The same from device-resident columns (`dtab`: name -> tensor, `ncomp` rows used)."""
+        torch = self.torch
+        keys, vals, cb = self.stamp_coo(dtab, ncomp, kcl, n, stride)
         rhs = self.empty(max(1, n), torch.float64)[:n]
         nnz = C.c_int64(0)
         p = self.ptr
@@ -235,6 +244,23 @@ class Device:
         self.torch.cuda.current_stream(self.dev).synchronize()
         del keys, vals
         return DeviceCSR(n, indptr, indices, data), rhs
+
+    def select_local(self, dtab, ncomp, rb, re):
+        """Columns of the components with a lead on a row in [rb, re), order kept, selected on the
+        device from the resident table (row-partitioned assembly).  Returns (columns, count)."""
+        torch = self.torch
+        pos = self.empty(max(1, ncomp), torch.int32)
+        count = C.c_int64(0)
+        p = self.ptr
+        _lib.check(self.lib.nodal_table_select_scan(self.ctx, ncomp, p(dtab["a"]), p(dtab["b"]), int(rb), int(re),
+                                                    p(pos), C.byref(count), self.stream()), "nodal_table_select_scan")
+        m = count.value
+        names = ("type", "value", "a", "b", "c", "d", "drv", "branch")
+        out = {k: self.empty(max(1, m), dtab[k].dtype) for k in names}
+        _lib.check(self.lib.nodal_table_select_gather(
+            self.ctx, ncomp, p(pos), int(rb), int(re), *[p(dtab[k]) for k in names], *[p(out[k]) for k in names],
+            self.stream()), "nodal_table_select_gather")
+        return out, m
 
     def csr_to_dense(self, csr: DeviceCSR):
         n = csr.n

@@ -1,4 +1,4 @@
-"""Multi-GPU path: row-partitioned Jacobi-PCG, one process per GPU.
+"""Multi-GPU path: row-partitioned Jacobi- and AMG-PCG, one process per GPU.
 
 Host side only does bookkeeping: the row partition, the per-rank slice of the component
 table (every component that touches a row the rank owns, in global stamping order, so the
@@ -85,6 +85,34 @@ class DistPCG:
         indptr = (ip - ip[0]).contiguous()
         return indptr, csr.indices[s:e], csr.data[s:e], rhs[rb:re]
 
+    AMG_PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max", "gather_below")
+
+    def solve_amg(self, n_global, bounds, indptr, indices, data, rhs_local, rtol=1e-10, maxit=None, **params):
+        """Row-partitioned AMG-preconditioned CG (csrc/dist_amg.cu)."""
+        dev, torch = self.dev, self.dev.torch
+        unknown = set(params) - set(self.AMG_PARAMS)
+        if unknown:
+            raise TypeError(f"unknown AMG parameter(s): {sorted(unknown)}")
+        nloc = int(bounds[self.rank + 1] - bounds[self.rank])
+        x = dev.zeros(max(2, nloc), torch.float64)[:nloc]
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        arr = (C.c_double * 8)(*[float(params.get(k, 0.0)) for k in self.AMG_PARAMS])
+        iters, relres = C.c_int32(0), C.c_double(0.0)
+        stats = (C.c_double * 32)()
+        p = dev.ptr
+        st = dev.lib.nodal_dist_amg_pcg(dev.ctx, self.handle, int(n_global), b.ctypes.data_as(C.c_void_p),
+                                        int(data.numel()), p(indptr), p(indices), p(data), p(rhs_local), p(x), arr,
+                                        rtol, int(maxit or 1000), C.byref(iters), C.byref(relres), stats, dev.stream())
+        _lib.check(st, "nodal_dist_amg_pcg", allowed=(_lib.OK, _lib.NOT_CONVERGED, _lib.BREAKDOWN))
+        nlev = int(stats[8]) + 1
+        info = dict(solver="dist_amg_pcg", status=st, iterations=iters.value, relres=relres.value,
+                    restarts=int(stats[2]), solve_ms=stats[3], setup_ms=stats[4], levels=int(stats[0]),
+                    distributed_levels=int(stats[8]), level_rows=[int(stats[16 + l]) for l in range(min(nlev, 12))],
+                    replicated_rows=int(stats[11]), coarsest_rows=int(stats[5]), coarsest_direct=bool(stats[7]),
+                    comm="p2p" if stats[9] else ("nccl" if self.world > 1 else "none"),
+                    kernels_per_iteration=int(stats[10]), halo_recv=int(stats[12]), nnz=int(data.numel()))
+        return x, info
+
     def solve(self, n_global, bounds, indptr, indices, data, rhs_local, rtol=1e-10, maxit=None):
         dev, torch = self.dev, self.dev.torch
         nloc = int(bounds[self.rank + 1] - bounds[self.rank])
@@ -109,52 +137,112 @@ class DistPCG:
         return x, info
 
 
-class GridRunner:
-    """bench.py's multi-GPU step: local stamp + CSR build + partitioned PCG + R on every rank."""
+class LocalRows:
+    """A rank's rows of G (row pointer rebased to 0, GLOBAL column indices, device tensors)."""
 
-    def __init__(self, dev, table, probe_row, rank, world, rtol=1e-10):
+    def __init__(self, n, bounds, rank, indptr, indices, data):
+        self.n, self.bounds, self.rank = int(n), bounds, int(rank)
+        self.indptr, self.indices, self.data = indptr, indices, data
+
+    @property
+    def nnz(self):
+        return int(self.data.numel())
+
+    @property
+    def shape(self):
+        return (int(self.bounds[self.rank + 1] - self.bounds[self.rank]), self.n)
+
+    def tocsr(self):
+        """Host scipy.sparse.csr_matrix of the rank's rows (container only)."""
+        import scipy.sparse as sps
+        return sps.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                              shape=self.shape)
+
+
+_SOLVERS = {}
+
+
+def shared_solver(dev, rank, world):
+    """One NCCL communicator (and one set of peer-mapped buffers) per device and process group:
+    creating them costs far more than a solve."""
+    key = (dev.index, int(rank), int(world))
+    if key not in _SOLVERS or not _SOLVERS[key].handle:
+        _SOLVERS[key] = DistPCG(dev, rank, world)
+    return _SOLVERS[key]
+
+
+class GridRunner:
+    """One rank of the row-partitioned equivalent-resistance step used by bench.py and by
+    Circuit(..., distributed=True): select the rank's components ON THE DEVICE from the full
+    table, stamp + build its rows, partitioned solve (Jacobi- or AMG-PCG), R on every rank."""
+
+    def __init__(self, dev, table, probe_row, rank, world, rtol=1e-10, precond="jacobi", amg=None, solver=None):
+        if not table.is_spd_structured():
+            raise NotImplementedError("row-partitioned solve is implemented for R / A netlists (PCG)")
         self.dev, self.rank, self.world, self.rtol = dev, rank, world, rtol
+        self.precond, self.amg = precond, dict(amg or {})
+        self.table = table
         self.n = table.n
         self.bounds = partition_rows(self.n, world)
-        rb, re = int(self.bounds[rank]), int(self.bounds[rank + 1])
-        self.local = local_component_table(table, rb, re)
         self.probe_row = int(probe_row)
         self.owner = int(np.searchsorted(self.bounds, self.probe_row, side="right") - 1)
-        self.pcg = DistPCG(dev, rank, world)
-        self.dtab = dev.upload_table(self.local)
+        self.pcg = solver if solver is not None else DistPCG(dev, rank, world)
         self._host_x = None
+        self.x_local = None
+
+    def close(self):
+        self.pcg.close()
 
     def step_e2e(self):
-        """Same step with HOST buffers: the rank's component table goes up from pinned host
-        memory and its slice of the solution comes back to pinned host memory."""
+        """Same step with HOST buffers: the whole component table goes up from pinned host memory
+        (every rank holds the netlist), the rank's slice of the solution comes back to pinned
+        host memory."""
         torch = self.dev.torch
-        if getattr(self.local, "_pinned", None) is None:
-            self.local.pin_memory()
+        if getattr(self.table, "_pinned", None) is None:
+            self.table.pin_memory()
+        if self._host_x is None:
             nloc = int(self.bounds[self.rank + 1] - self.bounds[self.rank])
             self._host_x = torch.empty(nloc, dtype=torch.float64).pin_memory()
-        return self.step(upload=True)
+        return self.step(self.dev.upload_table(self.table), download=True)
 
-    def step(self, _unused=None, upload=False):
+    def assemble(self, dtab):
+        """(indptr_local, indices_global, data, rhs_local) of the rank's rows from the resident table."""
+        from .device import coo_stride
+        dev = self.dev
+        rb, re = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        ncomp = len(self.table)
+        if self.world > 1:
+            dtab, ncomp = dev.select_local(dtab, ncomp, rb, re)
+        csr, rhs = dev.assemble_csr_raw(dtab, ncomp, self.table.kcl, self.n, coo_stride(self.table))
+        ip = csr.indptr[rb: re + 1]
+        s, e = int(ip[0]), int(ip[-1])
+        return (ip - ip[0]).contiguous(), csr.indices[s:e], csr.data[s:e], rhs[rb:re]
+
+    def step(self, dtab, download=False):
         import time
-        import torch.distributed as dist
         torch = self.dev.torch
         t0 = time.perf_counter()
-        dtab = self.dev.upload_table(self.local) if upload else self.dtab
-        indptr, indices, data, rhs = self.pcg.assemble_local(self.local, self.bounds, dtab=dtab)
+        indptr, indices, data, rhs = self.assemble(dtab)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        x, info = self.pcg.solve(self.n, self.bounds, indptr, indices, data, rhs, rtol=self.rtol)
+        if self.precond == "amg":
+            x, info = self.pcg.solve_amg(self.n, self.bounds, indptr, indices, data, rhs, rtol=self.rtol, **self.amg)
+        else:
+            x, info = self.pcg.solve(self.n, self.bounds, indptr, indices, data, rhs, rtol=self.rtol)
         t2 = time.perf_counter()
         info["assemble_wall_ms"] = (t1 - t0) * 1e3
         info["solve_wall_ms"] = (t2 - t1) * 1e3
-        if upload:
+        if download:
             self._host_x.copy_(x, non_blocking=True)
             torch.cuda.synchronize()
         r = torch.zeros(1, dtype=torch.float64, device=self.dev.dev)
         if self.rank == self.owner:
             r[0] = x[self.probe_row - int(self.bounds[self.rank])]
-        dist.broadcast(r, src=self.owner)
         nnz = torch.tensor([info["nnz"]], dtype=torch.int64, device=self.dev.dev)
-        dist.all_reduce(nnz)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(r, src=self.owner)
+            dist.all_reduce(nnz)
         info["nnz"] = int(nnz.item())
+        self.x_local = x
         return float(r.item()), info

@@ -275,12 +275,34 @@ class Circuit:
         self.table = table
         dev = Device.get(self.options.get("device"))
         self._dev = dev
-        if self.sparse:
+        self._dist = None
+        if self.options.get("distributed"):
+            G, A = self._build_distributed(dev, table)
+        elif self.sparse:
             G, A = dev.assemble_csr(table)
         else:
             G, A = dev.assemble_dense(table, atomic=bool(self.options.get("atomic_stamp", False)))
         logging.debug(f"currents={currents}")
         return [G, A, currents]
+
+    def _build_distributed(self, dev, table):
+        """Row-partitioned form (one process per GPU under torchrun, torch.distributed initialised
+        with the nccl backend): every rank holds the netlist, uploads the table, selects the
+        components touching its rows on the device and builds its rows of G only.  G is then a
+        LocalRows view (the rank's rows, global columns), A the rank's slice of the right-hand side."""
+        import torch.distributed as tdist
+        from . import dist as ndist
+        if not self.sparse:
+            raise ValueError("distributed=True needs sparse=True (the dense LU is single-GPU)")
+        if not (tdist.is_available() and tdist.is_initialized()):
+            raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+        rank, world = tdist.get_rank(), tdist.get_world_size()
+        runner = ndist.GridRunner(dev, table, 0, rank, world, rtol=self.options.get("rtol", 1e-10),
+                                  precond="jacobi" if self.options.get("precond") == "jacobi" else "amg",
+                                  amg=self.options.get("amg"), solver=ndist.shared_solver(dev, rank, world))
+        indptr, indices, data, rhs = runner.assemble(dev.upload_table(table))
+        self._dist = runner
+        return ndist.LocalRows(table.n, runner.bounds, rank, indptr, indices, data), rhs
 
     @property
     def A_host(self):
@@ -294,26 +316,53 @@ class Circuit:
 
     # ---- solve ------------------------------------------------------------------
     def _sparse_solver(self):
-        """Which device solver the sparse path uses: "amg", "pcg" or "gmres"."""
-        precond = self.options.get("precond", "jacobi")
-        if precond not in ("jacobi", "amg"):
-            raise ValueError(f"precond must be 'jacobi' or 'amg', got {precond!r}")
+        """Which device solver the sparse path uses: "amg", "pcg" or "gmres".
+        precond: "auto" (default) = aggregation-AMG preconditioned CG for R / A netlists, with a
+        Jacobi-PCG retry if the hierarchy cannot be built or the solve does not converge (the
+        behaviour on singular systems is then the Jacobi path's); "amg" / "jacobi" force one."""
+        precond = self.options.get("precond", "auto")
+        if precond not in ("auto", "jacobi", "amg"):
+            raise ValueError(f"precond must be 'auto', 'jacobi' or 'amg', got {precond!r}")
         if not self.table.is_spd_structured():
             return "gmres"
-        return "amg" if precond == "amg" else "pcg"
+        return "pcg" if precond == "jacobi" else "amg"
 
     def _device_solve(self, rhs, amg=None):
-        """x, info for G x = rhs on the device (rhs is a device tensor; dense G is not modified)."""
+        """x, info for G x = rhs on the device (rhs is a device tensor; dense G is not modified).
+        Distributed circuits: rhs and x are the rank's slices."""
         dev = self._dev
         if not self.sparse:
             return dev.lu_solve(self.G.clone(), rhs)
         kind = self._sparse_solver()
         rtol = self.options.get("rtol", 1e-10)
-        if kind == "amg" and amg is not None:
-            return amg.solve(rhs, rtol=rtol, maxit=self.options.get("maxit"))
+        if self._dist is not None:
+            if kind == "gmres":
+                raise NotImplementedError("row-partitioned solve is implemented for R / A netlists")
+            g, run = self.G, self._dist
+            if kind == "amg":
+                return run.pcg.solve_amg(g.n, g.bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol,
+                                         maxit=self.options.get("maxit"), **(self.options.get("amg") or {}))
+            return run.pcg.solve(g.n, g.bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol,
+                                 maxit=self.options.get("maxit"))
         if kind == "amg":
-            return dev.amg_pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
-                               **self.options.get("amg", {}))
+            from . import _lib
+            try:
+                if amg is not None:
+                    x, info = amg.solve(rhs, rtol=rtol, maxit=self.options.get("maxit"))
+                else:
+                    x, info = dev.amg_pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                                          **(self.options.get("amg") or {}))
+                if info["status"] == 0 or self.options.get("precond") == "amg":
+                    return x, info
+                first = f"amg_pcg status {info['status']} after {info['iterations']} iterations"
+            except _lib.NodalLibraryError as err:
+                if self.options.get("precond") == "amg":
+                    raise
+                first = str(err)
+            x, info = dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                              flags=self.options.get("pcg_flags", 0))
+            info["fallback_from_amg"] = first
+            return x, info
         if kind == "pcg":
             return dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
                            flags=self.options.get("pcg_flags", 0))
@@ -339,7 +388,7 @@ class Circuit:
             raise UnconnectedCircuitError
         x, info = self._device_solve(self.A)
         if self.sparse:
-            e = x.cpu().numpy()
+            e = self._dist_gather(x) if self._dist is not None else x.cpu().numpy()
             if info["status"] != 0:
                 # the reference's sparse path does not raise on singular systems: scipy warns
                 # (MatrixRankWarning) and returns NaNs.  Mirror that.
@@ -359,21 +408,57 @@ class Circuit:
         sol.stats = info
         return sol
 
+    def _dist_gather(self, x_local):
+        """The whole solution vector on the host of every rank (slices all-gathered on the device)."""
+        import torch.distributed as tdist
+        torch, run = self._dev.torch, self._dist
+        world = run.world
+        sizes = np.diff(run.bounds).astype(np.int64)
+        if world == 1:
+            return x_local.cpu().numpy()
+        pad = int(sizes.max())
+        mine = torch.zeros(pad, dtype=torch.float64, device=self._dev.dev)
+        mine[: x_local.numel()] = x_local
+        full = torch.empty(world * pad, dtype=torch.float64, device=self._dev.dev)
+        tdist.all_gather_into_tensor(full, mine)
+        host = full.cpu().numpy().reshape(world, pad)
+        return np.concatenate([host[k, : sizes[k]] for k in range(world)])
+
     def port_resistances(self, pairs):
         """e(a) - e(b) for a 1 A source from b to a, for every (a, b) in `pairs`, against the
         matrix assembled once (many-port equivalent resistance).
-        Only the two potentials of a pair leave the device.  The AMG hierarchy (precond="amg")
-        is built once and shared by all right-hand sides."""
+        Only the two potentials of a pair leave the device.  The AMG hierarchy is built once
+        and shared by all right-hand sides."""
         dev, torch = self._dev, self._dev.torch
         n = self.table.n
         net = self.netlist
+        run = self._dist
+        lo, hi = (int(run.bounds[run.rank]), int(run.bounds[run.rank + 1])) if run is not None else (0, n)
 
         def row(node):
             return c.GROUND if node == net.ground else net.nodenum[node]
 
+        def value_at(x, i):
+            if i == c.GROUND:
+                return 0.0
+            if run is None or run.world == 1:
+                return float(x[i - lo])
+            import torch.distributed as tdist
+            v = torch.zeros(1, dtype=torch.float64, device=dev.dev)
+            if lo <= i < hi:
+                v[0] = x[i - lo]
+            tdist.broadcast(v, src=int(np.searchsorted(run.bounds, i, side="right") - 1))
+            return float(v.item())
+
         amg = None
-        if self.sparse and self._sparse_solver() == "amg":
-            amg = dev.amg(self.G, **self.options.get("amg", {}))
+        if self.sparse and run is None and self._sparse_solver() == "amg":
+            from . import _lib
+            try:
+                amg = dev.amg(self.G, **(self.options.get("amg") or {}))
+            except _lib.NodalLibraryError:
+                if self.options.get("precond") == "amg":
+                    raise
+                amg = None             # _device_solve retries per right-hand side and falls back to Jacobi
         values, stats = [], []
         try:
             for a, b in pairs:
@@ -382,19 +467,17 @@ class Circuit:
                     values.append(0.0)
                     stats.append(dict(solver="none", status=0, iterations=0))
                     continue
-                rhs = dev.zeros(max(2, n), torch.float64)[:n]
-                if ia != c.GROUND:
-                    rhs[ia] = 1.0
-                if ib != c.GROUND:
-                    rhs[ib] = -1.0
+                rhs = dev.zeros(max(2, hi - lo), torch.float64)[: hi - lo]
+                if ia != c.GROUND and lo <= ia < hi:
+                    rhs[ia - lo] = 1.0
+                if ib != c.GROUND and lo <= ib < hi:
+                    rhs[ib - lo] = -1.0
                 x, info = self._device_solve(rhs, amg=amg)
                 if not self.sparse and info["status"] == 1:
                     raise np.linalg.LinAlgError("Singular matrix")
                 if self.sparse and info["status"] != 0:
                     warnings.warn(f"sparse solve did not converge ({info})", RuntimeWarning)
-                ea = float(x[ia]) if ia != c.GROUND else 0.0
-                eb = float(x[ib]) if ib != c.GROUND else 0.0
-                values.append(ea - eb)
+                values.append(value_at(x, ia) - value_at(x, ib))
                 stats.append(info)
         finally:
             if amg is not None:

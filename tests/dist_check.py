@@ -3,9 +3,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tests/dist_check.py [N]
 
-Every rank assembles its rows, solves the N x N grid with the partitioned PCG and the result
-is compared with the reference goldens and, for small N, with the
-single-GPU solve of rank 0."""
+Every rank assembles its rows, solves the N x N grid with the partitioned Jacobi-PCG and with the
+partitioned AMG-PCG (replicated, distributed and single-pass hierarchies) and the result is
+compared with the reference goldens and, for small N, with the single-GPU
+solves of rank 0.  NODAL_DIST_NO_P2P=1 runs the same over NCCL instead of peer memory."""
 import copy
 import json
 import os
@@ -36,24 +37,40 @@ def main():
         net = copy.deepcopy(gen.grid2d(N))
         net.process_component(["a1", "A", "1", "1", "g"])
         table = net.table()
-        runner = ndist.GridRunner(dev, table, net.nodenum["1"], rank, world, rtol=1e-10)
-        r, info = runner.step()
-        x_loc, _ = None, None
-        msg = dict(N=N, world=world, R=r, iterations=info["iterations"], relres=info["relres"],
-                   status=info["status"], halo_recv=info["halo_recv"], solve_ms=info["solve_ms"], comm=info["comm"])
-        if N in GOLD:
-            msg["rel_err_vs_reference"] = abs(r - GOLD[N]) / GOLD[N]
-            ok &= msg["rel_err_vs_reference"] < 1e-9
-        ok &= info["status"] == 0 and info["relres"] <= 1e-10
+        single = None
         if rank == 0 and N <= 400:
             csr, rhs = dev.assemble_csr(table)
             x1, i1 = dev.pcg(csr, rhs, rtol=1e-10)
-            msg["single_gpu_R"] = float(x1[net.nodenum["1"]])
-            msg["single_gpu_iterations"] = i1["iterations"]
-            ok &= abs(msg["single_gpu_R"] - r) < 1e-9
-        runner.pcg.close()
-        if rank == 0:
-            print(json.dumps(msg), flush=True)
+            x2, i2 = dev.amg_pcg(csr, rhs, rtol=1e-10)
+            single = dict(R=float(x1[net.nodenum["1"]]), iterations=i1["iterations"],
+                          R_amg=float(x2[net.nodenum["1"]]), iterations_amg=i2["iterations"])
+        # Jacobi form, then the AMG form with everything replicated (gather_below above n), with
+        # distributed levels down to ~n/40 rows, and with a single pairwise pass per level
+        dtab = dev.upload_table(table)
+        variants = [("jacobi", {}), ("amg", {}), ("amg", {"gather_below": max(300, N * N // 40)}),
+                    ("amg", {"gather_below": max(300, N * N // 6), "passes": 1})]
+        for precond, amg in variants:
+            runner = ndist.GridRunner(dev, table, net.nodenum["1"], rank, world, rtol=1e-10, precond=precond, amg=amg)
+            r, info = runner.step(dtab)
+            msg = dict(N=N, world=world, precond=precond, amg=amg, R=r, iterations=info["iterations"],
+                       relres=info["relres"], status=info["status"], halo_recv=info["halo_recv"],
+                       solve_ms=info["solve_ms"], setup_ms=info["setup_ms"], comm=info["comm"])
+            if precond == "amg":
+                msg.update(levels=info["levels"], distributed_levels=info["distributed_levels"],
+                           level_rows=info["level_rows"], replicated_rows=info["replicated_rows"])
+            if N in GOLD:
+                msg["rel_err_vs_reference"] = abs(r - GOLD[N]) / GOLD[N]
+                ok &= msg["rel_err_vs_reference"] < 1e-9
+            ok &= info["status"] == 0 and info["relres"] <= 1e-10
+            if single is not None:
+                msg["single_gpu"] = single
+                ok &= abs(single["R"] - r) < 1e-9
+                if precond == "amg" and amg.get("passes", 2) == 2:
+                    # rank-local aggregation costs a few iterations at most (tests/study_partitioned_aggregation.py)
+                    ok &= info["iterations"] <= single["iterations_amg"] + 8
+            runner.pcg.close()
+            if rank == 0:
+                print(json.dumps(msg), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -171,3 +171,36 @@ def test_many_port_equivalent_resistances(device, mode):
     assert got[0] == pytest.approx(got[1], rel=1e-12)    # symmetric in (a, b)
     with pytest.raises(KeyError):
         n.equiv.equivalent_resistances(net, [("1", "nowhere")], **kw)
+
+
+# ------------------------------------------------------------------ row-partitioned form, one rank
+@pytest.mark.parametrize("N,amg", [(100, {}), (100, {"gather_below": 400}), (100, {"gather_below": 3000, "passes": 1}),
+                                   (400, {"gather_below": 5000}), (1000, {"gather_below": 20000})])
+def test_dist_amg_single_rank(device, N, amg):
+    """csrc/dist_amg.cu with a world of one rank (empty halos, no exchange) must reproduce the
+    single-GPU hierarchy: same level sizes where the levels are built the same way, same answer."""
+    import copy
+    from nodal_b200 import dist as ndist
+    net = copy.deepcopy(gen.grid2d(N))
+    net.process_component(["a1", "A", "1", "1", "g"])
+    table = net.table()
+    csr, rhs = device.assemble_csr(table)
+    x1, i1 = device.amg_pcg(csr, rhs, rtol=1e-10, **{k: v for k, v in amg.items() if k != "gather_below"})
+    solver = ndist.DistPCG(device, 0, 1)
+    try:
+        bounds = ndist.partition_rows(table.n, 1)
+        indptr, indices, data, rhs_l = solver.assemble_local(table, bounds)
+        x, info = solver.solve_amg(table.n, bounds, indptr, indices, data, rhs_l, rtol=1e-10, **amg)
+    finally:
+        solver.close()
+    assert info["status"] == 0 and info["relres"] <= 1e-10, info
+    if "gather_below" in amg:
+        assert info["distributed_levels"] >= 1, info
+    # one rank: the aggregates are the single-GPU ones, level for level
+    assert info["level_rows"] == i1["level_rows"][: info["distributed_levels"] + 1], (info, i1)
+    assert abs(info["iterations"] - i1["iterations"]) <= 2
+    want = {100: GRIDS["grid2d_100"]["R_sparse"], 400: 0.7732566450916762, 1000: 0.7732422803670024}[N]
+    assert float(x[net.nodenum["1"]]) == pytest.approx(want, rel=1e-9)
+    resid = device.spmv(csr, x) - rhs
+    assert float(resid.norm() / rhs.norm()) <= 1.05e-10
+    assert float((x - x1).abs().max()) <= 1e-8 * float(x1.abs().max())

@@ -205,6 +205,14 @@ int nodal_lu_batched(nodal_ctx* ctx, int64_t batch, int32_t ncomp,
                      int32_t kcl, int32_t n, const double* values, double* x, int32_t* info,
                      void* stream);
 
+/* The same with the transposed (structure-of-arrays) layout: values_t is ncomp x batch and x_t is
+ * n x batch, system index fastest, so a warp's loads and stores are contiguous.  n <= 8. */
+int nodal_lu_batched_soa(nodal_ctx* ctx, int64_t batch, int32_t ncomp,
+                         const uint8_t* type, const int32_t* a, const int32_t* b,
+                         const int32_t* c, const int32_t* d, const int32_t* drv, const int32_t* branch,
+                         int32_t kcl, int32_t n, const double* values_t, double* x_t, int32_t* info,
+                         void* stream);
+
 /* ---------------------------------------------------------------- multi-GPU
  * Row-partitioned PCG: rank k owns rows [bounds[k], bounds[k+1]) of the global
  * system as a local CSR whose column indices are GLOBAL.  Halo exchange of the

@@ -52,6 +52,8 @@ SIGNATURES = {
     "nodal_lu_solve": (C.c_int, [_vp, _i32, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
     "nodal_lu_batched": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _i32, _i32, _vp, _vp, _vp, _vp]),
+    "nodal_lu_batched_soa": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _i32, _i32, _vp, _vp, _vp, _vp]),
     "nodal_dist_unique_id": (C.c_int, [_vp]),
     "nodal_dist_create": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
     "nodal_dist_destroy": (C.c_int, [_vp]),

@@ -36,6 +36,7 @@ extern "C" int nodal_ctx_create(int device, nodal_ctx** out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaMallocHost(&ctx->pinned, 4096));
+    memset(ctx->pinned, 0, 4096);
     *out = ctx;
     return NODAL_OK;
 }

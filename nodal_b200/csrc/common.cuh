@@ -147,3 +147,4 @@ size_t scan_scratch_bytes(int64_t count);
 int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* vals_alt,
                      int64_t count, int bits, bool* result_in_alt, cudaStream_t st);
 size_t radix_sort_scratch_bytes(int64_t count);
+int radix_sort_check(nodal_ctx* ctx);   // after a stream sync: NODAL_CUDA_ERROR if a sort pass gave up

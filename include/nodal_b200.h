@@ -69,6 +69,9 @@ int64_t nodal_ctx_workspace_bytes(nodal_ctx* ctx);
  * (R 4, A 2, E 5, VCVS/VCCS/CCVS 6, CCCS 5); colbits = bits needed for n.
  * Within-component '=' / '+=' ordering of the reference is resolved here, so
  * the later reduction is a pure in-order sum.
+ * c, d, drv and branch may be NULL when the table holds only R and A rows (the columns are
+ * then the constants NODAL_UNUSED / -1 and are not read): 17 instead of 33 bytes per component.
+ * The same holds for nodal_lu_batched* and nodal_table_select_gather.
  */
 int nodal_stamp_coo(nodal_ctx* ctx, int64_t ncomp,
                     const uint8_t* type, const double* value,
@@ -223,6 +226,9 @@ typedef struct nodal_dist nodal_dist;
 int nodal_dist_unique_id(uint8_t id_h[128]);
 int nodal_dist_create(nodal_ctx* ctx, const uint8_t id_h[128], int32_t rank, int32_t nranks,
                       nodal_dist** out);
+/* one rank, no communicator, libnccl not needed: nodal_dist_amg_pcg then is the graph-captured
+ * single-GPU AMG-PCG (nodal_dist_pcg needs a communicator) */
+int nodal_dist_create_single(nodal_ctx* ctx, nodal_dist** out);
 int nodal_dist_destroy(nodal_dist* d);
 /* bounds_h[nranks + 1]: row partition, bounds_h[0] = 0, bounds_h[nranks] = n_global (host).
  * indptr is the local row pointer rebased to 0 (length nloc + 1), nnz = indptr[nloc].

@@ -56,6 +56,7 @@ SIGNATURES = {
                                        _i32, _i32, _vp, _vp, _vp, _vp]),
     "nodal_dist_unique_id": (C.c_int, [_vp]),
     "nodal_dist_create": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "nodal_dist_create_single": (C.c_int, [_vp, C.POINTER(_vp)]),
     "nodal_dist_destroy": (C.c_int, [_vp]),
     "nodal_dist_pcg": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _f64, _i32,
                                  C.POINTER(_i32), C.POINTER(_f64), C.POINTER(_f64), _vp]),

@@ -136,7 +136,7 @@ amg_jacobi0_kernel(int32_t n, const double* __restrict__ dinv, const double* __r
 //   MODE 1: y = b - A x                                   (residual)
 //   MODE 2: y = x + omega D^-1 (b - A x)                  (damped Jacobi sweep, out of place)
 template <int MODE>
-static __global__ void __launch_bounds__(AT, 4)
+static __global__ void __launch_bounds__(AT, 5)
 amg_sell_kernel(int32_t n, int32_t nslices, const u32* __restrict__ slice_w,
                 const int32_t* __restrict__ cols, const double* __restrict__ vals,
                 const double* __restrict__ dinv, const double* __restrict__ b,

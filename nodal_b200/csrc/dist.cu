@@ -104,6 +104,18 @@ extern "C" int nodal_dist_create(nodal_ctx* ctx, const uint8_t* id_h, int32_t ra
     return NODAL_OK;
 }
 
+// A one-rank object without a communicator (no NCCL needed): the row-partitioned drivers run
+// with empty halos, which makes nodal_dist_amg_pcg the graph-captured single-GPU AMG-PCG.
+extern "C" int nodal_dist_create_single(nodal_ctx* ctx, nodal_dist** out) {
+    if (!ctx || !out) return NODAL_BAD_ARG;
+    nodal_dist* d = new nodal_dist();
+    d->rank = 0;
+    d->nranks = 1;
+    d->device = ctx->device;
+    *out = d;
+    return NODAL_OK;
+}
+
 extern "C" int nodal_dist_destroy(nodal_dist* d) {
     if (!d) return NODAL_OK;
     cudaSetDevice(d->device);
@@ -813,6 +825,10 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
                               double rtol, int32_t maxit, int32_t* iters_h, double* relres_h,
                               double* stats_h, void* stream) {
     if (!ctx || !d || !bounds_h || !iters_h || !relres_h) return NODAL_BAD_ARG;
+    if (!d->comm) {
+        nodal_set_error("nodal_dist_pcg needs a communicator (nodal_dist_create); use nodal_pcg on one GPU");
+        return NODAL_BAD_ARG;
+    }
     *iters_h = 0;
     *relres_h = 0.0;
     if (stats_h) memset(stats_h, 0, 16 * sizeof(double));

@@ -239,7 +239,7 @@ acg_vector_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur,
 }
 
 // w = A u (SELL-32, one warp per slice) + partial sums of r.u and w.u
-__global__ void __launch_bounds__(DA, 4)
+__global__ void __launch_bounds__(DA, 5)
 acg_spmv_dots_kernel(int32_t n, int32_t nslices, const u32* __restrict__ slice_w, const int32_t* __restrict__ cols,
                      const double* __restrict__ vals, const double* __restrict__ u, const double* __restrict__ r,
                      double* __restrict__ w, double* __restrict__ part_g, double* __restrict__ part_d) {

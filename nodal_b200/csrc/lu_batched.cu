@@ -28,9 +28,9 @@ __global__ void lu_batched_kernel(int64_t batch, int ncomp, const uint8_t* __res
         for (int k = 0; k < ncomp; ++k) {
             const int t = type[k];
             double dv = 1.0;
-            if (t == NODAL_T_CCVS || t == NODAL_T_CCCS) dv = val[drv[k]];
-            StampOut o;
-            stamp_component(t, val[k], a[k], b[k], c[k], d[k], dv, branch[k], kcl, n, o);
+            if ((t == NODAL_T_CCVS || t == NODAL_T_CCCS) && drv) dv = val[drv[k]];
+            StampOut o;    // c / d / drv / branch may be null for R / A-only topologies
+            stamp_component(t, val[k], a[k], b[k], c ? c[k] : -2, d ? d[k] : -2, dv, branch ? branch[k] : -1, kcl, n, o);
             for (int e = 0; e < o.count; ++e) AT(o.row[e], o.col[e]) += o.val[e];   // col == n is the rhs
         }
         int bad = 0;
@@ -107,9 +107,10 @@ lu_batched_reg_kernel(int64_t batch, int ncomp, const uint8_t* __restrict__ type
         for (int k = 0; k < ncomp; ++k) {
             const int t = type[k];
             double dv = 1.0;
-            if (t == NODAL_T_CCVS || t == NODAL_T_CCCS) dv = val[(int64_t)drv[k] * vs];
+            if ((t == NODAL_T_CCVS || t == NODAL_T_CCCS) && drv) dv = val[(int64_t)drv[k] * vs];
             StampOut o;
-            stamp_component(t, val[(int64_t)k * vs], a[k], b[k], c[k], d[k], dv, branch[k], kcl, N, o);
+            stamp_component(t, val[(int64_t)k * vs], a[k], b[k], c ? c[k] : -2, d ? d[k] : -2, dv,
+                            branch ? branch[k] : -1, kcl, N, o);
             static_for<6>([&](auto E) {          // a component emits at most 6 entries (stamp_core.cuh)
                 constexpr int e = E;
                 if (e < o.count) M[(o.row[e] * LD + o.col[e]) * T + tid] += o.val[e];   // col == N is the rhs

@@ -32,8 +32,10 @@ stamp_coo_kernel(int64_t ncomp, const uint8_t* __restrict__ type, const double* 
         if (i < ncomp) {
             const int t = type[i];
             double dv = 1.0;
-            if (t == NODAL_T_CCVS || t == NODAL_T_CCCS) dv = value[drv[i]];
-            stamp_component(t, value[i], a[i], b[i], c[i], d[i], dv, branch[i], kcl, n, o);
+            if ((t == NODAL_T_CCVS || t == NODAL_T_CCCS) && drv) dv = value[drv[i]];
+            // c / d / drv / branch may be null for R / A-only tables (the columns hold constants
+            // then and are neither uploaded nor read: 17 instead of 33 bytes per component)
+            stamp_component(t, value[i], a[i], b[i], c ? c[i] : -2, d ? d[i] : -2, dv, branch ? branch[i] : -1, kcl, n, o);
         }
 #pragma unroll
         for (int k = 0; k < STRIDE; ++k) {
@@ -113,7 +115,10 @@ select_gather_kernel(int64_t ncomp, const u32* __restrict__ pos, int32_t rb, int
         if (!((x >= rb && x < re) || (y >= rb && y < re))) continue;
         const u32 p = pos[i];
         o_type[p] = type[i]; o_value[p] = value[i]; o_a[p] = x; o_b[p] = y;
-        o_c[p] = c[i]; o_d[p] = d[i]; o_drv[p] = drv[i]; o_branch[p] = branch[i];
+        if (c) o_c[p] = c[i];
+        if (d) o_d[p] = d[i];
+        if (drv) o_drv[p] = drv[i];
+        if (branch) o_branch[p] = branch[i];
     }
 }
 

@@ -198,13 +198,28 @@ class Device:
 
     @staticmethod
     def ptr(t):
-        return C.c_void_p(t.data_ptr())
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
     def upload_table(self, table: ComponentTable, pin=False):
+        """Columns of the table in HBM.  R / A-only tables (the SPD path) carry constants in the
+        c / d / drv / branch columns: those are not uploaded (the kernels take null pointers for
+        them), 17 instead of 33 bytes per component."""
+        names = ("type", "value", "a", "b", "c", "d", "drv", "branch")
+        if table.is_spd_structured():
+            names = names[:4]
         if getattr(table, "_pinned", None):
-            return {name: t.to(self.dev, non_blocking=True) for name, t in table._pinned.items()}
-        return {name: self.to_device(getattr(table, name), pin=pin)
-                for name in ("type", "value", "a", "b", "c", "d", "drv", "branch")}
+            out = {name: table._pinned[name].to(self.dev, non_blocking=True) for name in names}
+        else:
+            out = {name: self.to_device(getattr(table, name), pin=pin) for name in names}
+        for name in ("c", "d", "drv", "branch"):
+            out.setdefault(name, None)
+        return out
+
+    @staticmethod
+    def uploaded_bytes(table: ComponentTable):
+        """Bytes upload_table moves for this table."""
+        per_row = 17 if table.is_spd_structured() else 33
+        return per_row * len(table)
 
     # ------------------------------------------------------------ stamping
     def stamp_coo(self, dtab, ncomp, kcl, n, stride):
@@ -256,7 +271,7 @@ class Device:
                                                     p(pos), C.byref(count), self.stream()), "nodal_table_select_scan")
         m = count.value
         names = ("type", "value", "a", "b", "c", "d", "drv", "branch")
-        out = {k: self.empty(max(1, m), dtab[k].dtype) for k in names}
+        out = {k: (self.empty(max(1, m), dtab[k].dtype) if dtab[k] is not None else None) for k in names}
         _lib.check(self.lib.nodal_table_select_gather(
             self.ctx, ncomp, p(pos), int(rb), int(re), *[p(dtab[k]) for k in names], *[p(out[k]) for k in names],
             self.stream()), "nodal_table_select_gather")

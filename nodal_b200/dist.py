@@ -69,6 +69,17 @@ class DistPCG:
         _lib.check(lib.nodal_dist_create(dev.ctx, raw, self.rank, self.world, C.byref(h)), "nodal_dist_create")
         self.handle = h
 
+    @classmethod
+    def single(cls, dev):
+        """One rank without a communicator (libnccl is not loaded): only solve_amg works, as the
+        graph-captured single-GPU AMG-PCG."""
+        self = cls.__new__(cls)
+        self.dev, self.rank, self.world = dev, 0, 1
+        h = C.c_void_p()
+        _lib.check(dev.lib.nodal_dist_create_single(dev.ctx, C.byref(h)), "nodal_dist_create_single")
+        self.handle = h
+        return self
+
     def close(self):
         if self.handle:
             self.dev.lib.nodal_dist_destroy(self.handle)
@@ -168,6 +179,14 @@ def shared_solver(dev, rank, world):
     key = (dev.index, int(rank), int(world))
     if key not in _SOLVERS or not _SOLVERS[key].handle:
         _SOLVERS[key] = DistPCG(dev, rank, world)
+    return _SOLVERS[key]
+
+
+def single_solver(dev):
+    """The communicator-free one-rank solver object of this device (graph-captured AMG-PCG)."""
+    key = (dev.index, "single")
+    if key not in _SOLVERS or not _SOLVERS[key].handle:
+        _SOLVERS[key] = DistPCG.single(dev)
     return _SOLVERS[key]
 
 

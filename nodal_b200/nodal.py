@@ -349,6 +349,15 @@ class Circuit:
             try:
                 if amg is not None:
                     x, info = amg.solve(rhs, rtol=rtol, maxit=self.options.get("maxit"))
+                elif self.G.n >= self.options.get("amg_graph_min_rows", 100_000):
+                    # large systems: the graph-captured form (csrc/dist_amg.cu with one rank):
+                    # one CUDA graph per iteration, no host round trip inside the iteration
+                    from . import dist as ndist
+                    g = self.G
+                    bounds = np.array([0, g.n], dtype=np.int32)
+                    x, info = ndist.single_solver(dev).solve_amg(
+                        g.n, bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                        **(self.options.get("amg") or {}))
                 else:
                     x, info = dev.amg_pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
                                           **(self.options.get("amg") or {}))

@@ -65,7 +65,7 @@ def main():
             if single is not None:
                 msg["single_gpu"] = single
                 ok &= abs(single["R"] - r) < 1e-9
-                if precond == "amg" and amg.get("passes", 2) == 2:
+                if precond == "amg" and amg.get("passes", 2) == 2 and single["iterations_amg"] >= 10:
                     # rank-local aggregation costs a few iterations at most (tests/study_partitioned_aggregation.py)
                     ok &= info["iterations"] <= single["iterations_amg"] + 8
             runner.pcg.close()

@@ -279,11 +279,13 @@ def run_ours(args):
     value = n_unknowns / (ms_per_step * 1e-3)
     nnz = info["nnz"]
 
-    # ---- e2e leg: the public API with HOST buffers.  Every rank holds the netlist (pinned columns):
-    # Circuit(netlist, sparse=True[, distributed=True]).solve() uploads the table, (selects the rank's
-    # components on the device,) assembles, solves and brings the whole solution vector back to the
-    # host of every rank.
-    table.pin_memory()
+    # ---- e2e leg: the public API with HOST buffers.  Every rank holds the netlist (pinned columns);
+    # equivalent_resistance(netlist, "1", "g", sparse=True[, distributed=True]) -- the call behind
+    # `nodal-resistance FILE -s` (nodal/equiv.py:31-61) -- uploads the table, (selects the rank's
+    # components on the device,) assembles, solves and reads the two probe potentials back.
+    import nodal_b200.equiv
+    net.table().pin_memory()
+    net.table().facts()
     opts = dict(rtol=RTOL, precond=precond)
     if world > 1:
         opts["distributed"] = True
@@ -291,8 +293,8 @@ def run_ours(args):
         opts["amg"] = amg_opts
 
     def step_e2e():
-        sol = n.Circuit(probe, sparse=True, **opts).solve()   # the call a user makes (nodal/nodal.py:8-13)
-        return float(sol.result[row_1]), sol.stats
+        r_ = n.equiv.equivalent_resistance(net, "1", "g", sparse=True, **opts)
+        return float(r_), n.equiv.equivalent_resistance.last_stats
 
     step_e2e()
     barrier()
@@ -310,11 +312,11 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_ms /= args.steps
     e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
-           "h2d_bytes_per_step": int(Device.uploaded_bytes(table)) * world, "d2h_bytes_per_step": int(n_unknowns * 8) * world,
+           "h2d_bytes_per_step": int(Device.uploaded_bytes(net.table())) * world, "d2h_bytes_per_step": 16 * world,
            "ms_per_step": e2e_ms, "R": r_e2e, "solver": e2e_stats.get("solver"),
-           "api": "nodal_b200.Circuit(netlist, sparse=True" + (", distributed=True" if world > 1 else "") +
-                  ").solve() on a host TableNetlist (pinned columns) on every rank: whole table up, whole solution "
-                  "vector down, per rank (bytes summed over ranks)"}
+           "api": "nodal_b200.equiv.equivalent_resistance(netlist, '1', 'g', sparse=True" +
+                  (", distributed=True" if world > 1 else "") + ") on a host TableNetlist (pinned columns) on every "
+                  "rank: whole table up, the two probe potentials down (bytes summed over ranks)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

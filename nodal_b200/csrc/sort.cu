@@ -297,6 +297,7 @@ constexpr int OS_THREADS = 512;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_IPT = 8;
 constexpr int OS_TILE = OS_THREADS * OS_IPT;
+constexpr int OS_LOOK = 8;
 static_assert(OS_TILE == RS_TILE, "tile descriptors are sized with RS_TILE");
 
 __global__ void __launch_bounds__(OS_THREADS, 2)
@@ -363,16 +364,34 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u64* __restrict__ va
             digit_start[dgt] = start;
             u32 excl = 0;
             if (tile > 0) {
+                // Look-back in windows of OS_LOOK predecessors whose descriptor loads are all in
+                // flight at once: with ~300 tiles in flight the walk to the nearest inclusive
+                // prefix is dozens of steps, and one dependent L2 round trip per step made the
+                // look-back the longest phase of a tile.
                 const long long t0 = clock64();
-                for (int64_t t = tile - 1; t >= 0; --t) {
-                    const volatile u32* p = desc + (size_t)t * RS_BINS + dgt;
-                    u32 v = *p;
-                    while ((v >> 30) == 0u) {
-                        if (clock64() - t0 > OS_SPIN_LIMIT) { *err = 1; v = OS_INC; break; }
-                        v = *p;
+                bool done = false;
+                for (int64_t t = tile - 1; t >= 0 && !done; t -= OS_LOOK) {
+                    u32 v[OS_LOOK];
+#pragma unroll
+                    for (int k = 0; k < OS_LOOK; ++k) {
+                        const int64_t tt = t - k;
+                        v[k] = tt >= 0 ? *(const volatile u32*)(desc + (size_t)tt * RS_BINS + dgt) : OS_INC;
                     }
-                    excl += v & OS_VAL;
-                    if ((v >> 30) == 2u) break;
+#pragma unroll
+                    for (int k = 0; k < OS_LOOK; ++k) {
+                        if (done) continue;
+                        u32 x = v[k];
+                        if ((x >> 30) == 0u) {
+                            const volatile u32* p = desc + (size_t)(t - k) * RS_BINS + dgt;
+                            x = *p;
+                            while ((x >> 30) == 0u) {
+                                if (clock64() - t0 > OS_SPIN_LIMIT) { *err = 1; x = OS_INC; break; }
+                                x = *p;
+                            }
+                        }
+                        excl += x & OS_VAL;
+                        if ((x >> 30) == 2u) done = true;
+                    }
                 }
                 *mine = OS_INC | (excl + run);
             }

@@ -147,7 +147,7 @@ int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
                 double rtol, int32_t restart, int32_t maxit,
                 int32_t* iters_h, double* relres_h, void* stream);
 
-/* ---------------------------------------------------------------- AMG-preconditioned CG (opt-in)
+/* ---------------------------------------------------------------- AMG-preconditioned CG
  * Alternative to nodal_pcg for the same call site (`spsolve(G, A)`, nodal/nodal.py:325) on
  * symmetric positive definite systems: a V(1,1) cycle over pairwise aggregates (csrc/amg.cu)
  * replaces the Jacobi preconditioner, so the iteration count stays nearly flat in n.
@@ -156,7 +156,9 @@ int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
  * stay alive and unchanged until nodal_amg_destroy).  params is NULL or 8 doubles, 0 = default:
  * [0] pairwise passes per level (2), [1] stop coarsening at this many rows (512), [2] Jacobi
  * damping (0.8), [3] coarse-correction scale (1.8), [4] max levels (30), [5] handshake rounds
- * (8), [6] largest coarsest level that is inverted explicitly (2048), [7] reserved.
+ * (8), [6] largest coarsest level that is inverted explicitly (2048), [7] max_fill: coarsening stops
+ * when a coarser operator would keep more than this fraction of the entries (0.7; graphs that
+ * fill in instead of shrinking).
  * nodal_amg_info: level count, rows / nnz per level (up to cap entries), setup time, whether the
  * coarsest level is solved exactly.  nodal_amg_fetch_level copies a level's aggregate map
  * (agg, n entries; not on the coarsest level) and/or CSR arrays to device buffers (NULL = skip).
@@ -263,7 +265,8 @@ int nodal_table_select_gather(nodal_ctx* ctx, int64_t ncomp, const uint32_t* pos
  * nodal_dist_pcg, same call it replaces (spsolve, nodal/nodal.py:325, for R / A netlists).  Aggregates
  * never cross the partition; levels with at most params[7] global rows (default 400 000) are gathered
  * and handled by the single-GPU hierarchy replicated on every rank.  params (host, 8 doubles, 0 = default):
- * passes, coarse, omega, scale, maxlevels, rounds, direct_max (as nodal_amg_create), gather_below.
+ * passes, coarse, omega, scale, maxlevels, rounds, direct_max (as nodal_amg_create), gather_below,
+ * max_fill (9 doubles).
  * With one rank it is a graph-captured single-GPU form of nodal_amg_pcg.
  * stats_h (32 doubles): [0] levels, [2] restarts, [3] solve ms, [4] setup ms, [5] coarsest rows,
  * [7] coarsest solved directly, [8] distributed levels, [9] 2 = peer-memory exchanges / 0 = NCCL,

@@ -44,7 +44,7 @@ struct nodal_amg {
     nodal_ctx* ctx = nullptr;
     int device = 0;
     int passes = 2, coarse = 512, maxlevels = 30, rounds = 8, direct_max = 2048;
-    double omega = 0.8, scale = 1.8;
+    double omega = 0.8, scale = 1.8, max_fill = 0.7;
     std::vector<AmgLevel> lv;           // lv.back() is the coarsest level
     double* inv = nullptr;              // [nL x nL] inverse of the coarsest operator (or nullptr)
     double *p = nullptr, *q = nullptr, *r = nullptr, *z = nullptr;   // CG vectors
@@ -222,7 +222,10 @@ int build_hierarchy(nodal_amg* h, int32_t n, int64_t nnz, const int32_t* indptr,
             free_csr(ctx, A);
             A = Ac;
         }
-        if (rc != NODAL_OK || (double)A.n > 0.9 * (double)cur.n) {
+        // stalled: hardly fewer rows, or hardly fewer entries (expander-like graphs fill in: every
+        // coarse row couples to the union of its members' neighbourhoods and the hierarchy would
+        // cost more per level than it gains)
+        if (rc != NODAL_OK || (double)A.n > 0.9 * (double)cur.n || (double)A.nnz > h->max_fill * (double)cur.nnz) {
             free_csr(ctx, A);       // error, or coarsening stalled: cur stays the coarsest level
             ctx_pool_free(ctx, comp);
             if (rc != NODAL_OK) {
@@ -352,6 +355,7 @@ extern "C" int nodal_amg_create(nodal_ctx* ctx, int32_t n, int64_t nnz, const in
         if (params[4] >= 1.0) h->maxlevels = (int)params[4];
         if (params[5] >= 1.0) h->rounds = (int)params[5];
         if (params[6] >= 1.0) h->direct_max = (int)params[6];
+        if (params[7] > 0.0) h->max_fill = params[7];
     }
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));

@@ -412,7 +412,7 @@ struct Solver {
     int32_t* gather_need_dev = nullptr;   // [R] rows of every rank at the gathered level
     double* gather_stage = nullptr;       // NCCL path: R * gmax staging
     int32_t gmax = 0;
-    double omega = 0.8, scale = 1.8;
+    double omega = 0.8, scale = 1.8, max_fill = 0.7;
     int passes = 2, rounds = 8, maxlevels = 30;
     int64_t gather_below = 400000;
     double params_rep[8] = {0};
@@ -706,6 +706,19 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
         KERNEL_CHECK();
         NODAL_TRY(build_rows(S, nc_glob, nnz, cb, keys, vals, (*next_bounds)[S.me], ncur, next));
     }
+    {
+        // expander-like graphs fill in instead of shrinking: stop (same decision on every rank;
+        // counts in units of 1024 entries keep the all-gathered sums inside int32)
+        std::vector<int32_t> fine_k, coarse_k;
+        NODAL_TRY(gather_counts(S, (int32_t)(nnz >> 10) + 1, fine_k));
+        NODAL_TRY(gather_counts(S, (int32_t)(next->nnz >> 10) + 1, coarse_k));
+        if ((double)coarse_k[S.R] > S.max_fill * (double)fine_k[S.R]) {
+            amg_free_csr(ctx, *next);
+            ctx_pool_free(ctx, comp);
+            *stalled = true;
+            return NODAL_OK;
+        }
+    }
     L.agg = comp;
     S.owned.push_back(comp);
     L.nc = ncur;
@@ -857,9 +870,11 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
         if (params[5] >= 1.0) S.rounds = (int)params[5];
         direct_max = params[6];
         if (params[7] >= 1.0) S.gather_below = (int64_t)params[7];
+        if (params[8] > 0.0) S.max_fill = params[8];
     }
     S.params_rep[0] = S.passes; S.params_rep[1] = coarse; S.params_rep[2] = S.omega; S.params_rep[3] = S.scale;
     S.params_rep[4] = S.maxlevels; S.params_rep[5] = S.rounds; S.params_rep[6] = direct_max;
+    S.params_rep[7] = S.max_fill;
 
     cudaEvent_t ev0, ev1, ev2, ev_poll[2];
     CUDA_TRY(cudaEventCreate(&ev0));
@@ -908,6 +923,13 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
             S.lv.push_back(C);      // (invalidates L)
         }
         const int ND = (int)S.lv.size() - 1;
+        if (ND == 0 && (int64_t)S.lv[0].nglob > S.gather_below) {
+            // the finest level did not coarsen (stalled: hardly fewer rows or entries): replicating
+            // it on every rank would make every rank do the whole job.  Same decision everywhere.
+            nodal_set_error("nodal_dist_amg_pcg: the aggregation hierarchy stalled on the finest level "
+                            "(expander-like graph); use the Jacobi-preconditioned solver");
+            return NODAL_BREAKDOWN;
+        }
         if (2 * ND + 2 > AMG_SLOTS - 1) { nodal_set_error("nodal_dist_amg_pcg: too many distributed levels"); return NODAL_BAD_ARG; }
         // ---------------- replicated hierarchy below ----------------
         {

@@ -291,16 +291,19 @@ onesweep_bases_kernel(u32* __restrict__ ghist) {
     row[threadIdx.x] = ex;
 }
 
-// 512 threads x 8 keys per tile of 4096: 32 resident warps per SM at 2 CTAs / SM (the first
-// version, 256 x 16 at 128 registers, had 16 and spent 14.5 us per tile: 2.7 TB/s).
-constexpr int OS_THREADS = 512;
+// 256 threads x 8 keys per tile of 2048 at 4 CTAs / SM.  History (16.8 M-row grid, 134 M pairs,
+// ncu): 256 x 16 keys, 128 registers, 2 CTAs / SM: 1.60 ms per pass; 512 x 8, 2 CTAs / SM: 1.45 ms;
+// + windowed look-back: 1.34 ms = 3.2 TB/s with DRAM traffic equal to the algorithmic 4.3 GB --
+// warps stalled at the tile's barriers and on the loads in front of them (half of the issue
+// slots each), so more, smaller, independent CTAs per SM decorrelate the phases.
+constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_IPT = 8;
 constexpr int OS_TILE = OS_THREADS * OS_IPT;
 constexpr int OS_LOOK = 8;
-static_assert(OS_TILE == RS_TILE, "tile descriptors are sized with RS_TILE");
+constexpr int OS_CTAS_PER_SM = 4;
 
-__global__ void __launch_bounds__(OS_THREADS, 2)
+__global__ void __launch_bounds__(OS_THREADS, OS_CTAS_PER_SM)
 onesweep_pass_kernel(const u64* __restrict__ keys_in, const u64* __restrict__ vals_in,
                      u64* __restrict__ keys_out, u64* __restrict__ vals_out, int64_t count, int shift,
                      int64_t tiles, const u32* __restrict__ gbase /* [RS_BINS] exclusive */,
@@ -439,7 +442,7 @@ static bool use_legacy_sort() {
 }
 
 size_t radix_sort_scratch_bytes(int64_t count) {
-    const int64_t tiles = (count + RS_TILE - 1) / RS_TILE;
+    const int64_t tiles = (count + OS_TILE - 1) / OS_TILE;     // OS_TILE <= RS_TILE: covers both paths
     const size_t hist = align_up((size_t)tiles * RS_BINS * sizeof(u32), 256) + 256;
     return hist + scan_scratch_bytes(tiles * RS_BINS) + align_up(OS_MAXPASS * RS_BINS * sizeof(u32), 256) + 1024;
 }
@@ -450,8 +453,8 @@ int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* v
                      int64_t count, int bits, bool* result_in_alt, cudaStream_t st) {
     *result_in_alt = false;
     if (count <= 1 || bits <= 0) return NODAL_OK;
-    const int64_t tiles = (count + RS_TILE - 1) / RS_TILE;
-    if (tiles * RS_BINS >= (int64_t)1 << 32 || count >= (int64_t)1 << 30) {
+    int64_t tiles = (count + RS_TILE - 1) / RS_TILE;
+    if (tiles * RS_BINS * 2 >= (int64_t)1 << 32 || count >= (int64_t)1 << 30) {
         nodal_set_error("radix_sort_pairs: too many elements");
         return NODAL_BAD_ARG;
     }
@@ -477,6 +480,7 @@ int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* v
         return NODAL_OK;
     }
     // tile descriptors + ticket + error word (zeroed before every pass), digit bases of all passes
+    tiles = (count + OS_TILE - 1) / OS_TILE;
     const size_t desc_words = (size_t)tiles * RS_BINS + 64;
     u32* desc = carve<u32>(ctx, desc_words);
     u32* ghist = carve<u32>(ctx, OS_MAXPASS * RS_BINS);
@@ -486,7 +490,7 @@ int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* v
     // checked by radix_sort_check() after the caller's next stream synchronisation
     int* err = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned) + RADIX_ERR_OFFSET);
     static bool attr_set = false;
-    const size_t dyn = 2 * (size_t)RS_TILE * sizeof(u64);
+    const size_t dyn = 2 * (size_t)OS_TILE * sizeof(u64);
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         attr_set = true;
@@ -497,7 +501,7 @@ int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* v
     KERNEL_CHECK();
     onesweep_bases_kernel<<<passes, RS_BINS, 0, st>>>(ghist);
     KERNEL_CHECK();
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 2);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * OS_CTAS_PER_SM);
     for (int p = 0; p < passes; ++p) {
         CUDA_TRY(cudaMemsetAsync(desc, 0, desc_words * sizeof(u32), st));
         onesweep_pass_kernel<<<grid, OS_THREADS, dyn, st>>>(src_k, src_v, dst_k, dst_v, count, p * 8, tiles,

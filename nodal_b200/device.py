@@ -64,14 +64,14 @@ class DeviceCSR:
 class DeviceAMG:
     """Handle of a nodal_amg hierarchy; keeps the matrix arrays alive while it exists."""
 
-    PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max")
+    PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max", "max_fill")
 
     def __init__(self, dev, csr, **params):
         unknown = set(params) - set(self.PARAMS)
         if unknown:
             raise TypeError(f"unknown AMG parameter(s): {sorted(unknown)}")
         self.dev, self.csr = dev, csr
-        arr = (C.c_double * 8)(*[float(params.get(k, 0.0)) for k in self.PARAMS], 0.0)
+        arr = (C.c_double * 8)(*[float(params.get(k, 0.0)) for k in self.PARAMS])
         h = C.c_void_p()
         p = dev.ptr
         st = dev.lib.nodal_amg_create(dev.ctx, csr.n, csr.nnz, p(csr.indptr), p(csr.indices), p(csr.data),

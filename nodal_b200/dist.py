@@ -96,7 +96,7 @@ class DistPCG:
         indptr = (ip - ip[0]).contiguous()
         return indptr, csr.indices[s:e], csr.data[s:e], rhs[rb:re]
 
-    AMG_PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max", "gather_below")
+    AMG_PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max", "gather_below", "max_fill")
 
     def solve_amg(self, n_global, bounds, indptr, indices, data, rhs_local, rtol=1e-10, maxit=None, **params):
         """Row-partitioned AMG-preconditioned CG (csrc/dist_amg.cu)."""
@@ -107,7 +107,7 @@ class DistPCG:
         nloc = int(bounds[self.rank + 1] - bounds[self.rank])
         x = dev.zeros(max(2, nloc), torch.float64)[:nloc]
         b = np.ascontiguousarray(bounds, dtype=np.int32)
-        arr = (C.c_double * 8)(*[float(params.get(k, 0.0)) for k in self.AMG_PARAMS])
+        arr = (C.c_double * 9)(*[float(params.get(k, 0.0)) for k in self.AMG_PARAMS])
         iters, relres = C.c_int32(0), C.c_double(0.0)
         stats = (C.c_double * 32)()
         p = dev.ptr

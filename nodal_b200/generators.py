@@ -196,6 +196,64 @@ def lattice3d(N, resistance=1.0):
     return _lattice((N, N, N), (h, h, h), (h + 2, h + 1, h), resistance)
 
 
+# --------------------------------------------------------------------------- sparse random networks
+def random_network(nodes, degree=8, seed=0, decades=2.0, locality=None):
+    """Connected random resistive network (north star: "random-network netlists"): `nodes` nodes, a
+    spanning chain (node i to a random earlier node, which keeps it connected) plus random extra
+    resistors up to the average `degree`; resistances 10**U(0, decades) ohm.  Node "g" is node 0
+    and "1" is the last node.  Rows are numbered by the reference's first-appearance rule
+    (nodal/nodal.py:249-257,283-287) over the emitted component order, i.e. NOT geometrically:
+    the CSR's column indices and the halo sets of a row partition are irregular.
+
+    locality=None: the partner of every edge is uniform over all nodes (an expander-like graph:
+    every row block touches every other, the worst case for x gathers and halos).
+    locality=w: partners are drawn within +-w of the node id (a banded random graph, the shape a
+    placed-and-routed netlist has)."""
+    rng = np.random.default_rng(seed)
+    nodes = int(nodes)
+    chain_a = np.arange(1, nodes, dtype=np.int64)
+    if locality is None:
+        chain_b = (rng.random(nodes - 1) * chain_a).astype(np.int64)          # uniform in [0, i)
+    else:
+        chain_b = np.maximum(0, chain_a - 1 - (rng.random(nodes - 1) * np.minimum(chain_a, locality)).astype(np.int64))
+    extra = max(0, (degree * nodes) // 2 - (nodes - 1))
+    ea = rng.integers(0, nodes, size=extra, dtype=np.int64)
+    if locality is None:
+        eb = rng.integers(0, nodes, size=extra, dtype=np.int64)
+    else:
+        eb = np.clip(ea + rng.integers(-locality, locality + 1, size=extra, dtype=np.int64), 0, nodes - 1)
+    keep = ea != eb
+    # interleave the chain and the extra resistors so that first-appearance order is not simply
+    # the node order: component k of the chain is followed by its share of the extras
+    a_id = np.concatenate([chain_a, ea[keep]])
+    b_id = np.concatenate([chain_b, eb[keep]])
+    order = rng.permutation(len(a_id))
+    a_id, b_id = a_id[order], b_id[order]
+    gid, pid = 0, nodes - 1
+    index, kcl = first_appearance_numbering(a_id, b_id, gid)
+    m = len(a_id)
+    value = 10.0 ** rng.uniform(0.0, decades, size=m)
+    table = ComponentTable(np.full(m, K.T_R, np.uint8), value, index[a_id], index[b_id], kcl=kcl, be=0)
+
+    def encode(name):
+        if name == "1":
+            return pid
+        if name == "g":
+            return gid
+        if not name.startswith("n"):
+            return None
+        try:
+            nid = int(name[1:])
+        except ValueError:
+            return None
+        return nid if 0 < nid < nodes - 1 else None
+
+    def decode(nid):
+        return "1" if nid == pid else "g" if nid == gid else f"n{nid}"
+
+    return TableNetlist(table, _LazyNodeMap(index, encode, decode, kcl), "g", names=lambda k: f"r{k}")
+
+
 # --------------------------------------------------------------------------- config C3
 def random_opamp_network_rows(M=3968, P=2048, S=2048, V=64, seed=0, extra_degree=8):
     """Config C3: random connected resistive network with OPMODEL

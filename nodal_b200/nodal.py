@@ -339,11 +339,18 @@ class Circuit:
             if kind == "gmres":
                 raise NotImplementedError("row-partitioned solve is implemented for R / A netlists")
             g, run = self.G, self._dist
+            first = None
             if kind == "amg":
-                return run.pcg.solve_amg(g.n, g.bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol,
-                                         maxit=self.options.get("maxit"), **(self.options.get("amg") or {}))
-            return run.pcg.solve(g.n, g.bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol,
-                                 maxit=self.options.get("maxit"))
+                x, info = run.pcg.solve_amg(g.n, g.bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol,
+                                            maxit=self.options.get("maxit"), **(self.options.get("amg") or {}))
+                if info["status"] == 0 or self.options.get("precond") == "amg":
+                    return x, info
+                first = f"dist_amg_pcg status {info['status']}"      # same status on every rank
+            x, info = run.pcg.solve(g.n, g.bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol,
+                                    maxit=self.options.get("maxit"))
+            if first:
+                info["fallback_from_amg"] = first
+            return x, info
         if kind == "amg":
             from . import _lib
             try:

@@ -225,3 +225,22 @@ def test_config_c5a_full_size_properties(device):
     assert (r - limit) * N ** 2 == pytest.approx(c2000, rel=0.05)
     # every node potential lies between the two probe nodes' potentials (maximum principle)
     assert float(x.max()) <= r * (1 + 1e-9) and float(x.min()) >= -1e-9
+
+
+@pytest.mark.parametrize("locality", [None, 300])
+def test_random_network_equivalent_resistance(device, locality):
+    """Sparse random networks (first-appearance numbering, irregular columns): Jacobi-PCG, the
+    default (AMG with its fill-in guard and Jacobi fallback) and a direct CPU solve of the very
+    matrix the GPU assembled agree to 1e-9."""
+    import scipy.sparse.linalg as spla
+    tn = gen.random_network(30000, degree=8, seed=1, locality=locality)
+    circuit = n.Circuit(tn, sparse=True)
+    G = circuit.G_host.tocsc()
+    b = np.zeros(G.shape[0])
+    b[tn.nodenum["1"]] = 1.0
+    want = spla.spsolve(G, b)[tn.nodenum["1"]]
+    for precond in ("jacobi", "auto", "amg"):
+        r = n.equiv.equivalent_resistance(tn, "1", "g", sparse=True, precond=precond)
+        stats = n.equiv.equivalent_resistance.last_stats
+        assert stats["status"] == 0 and stats["relres"] <= 1e-10, (precond, stats)
+        assert r == pytest.approx(want, rel=1e-9), precond

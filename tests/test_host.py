@@ -172,6 +172,32 @@ def test_generated_tables_match_csv_path(key, tmp_path):
     assert "n999_0" not in tn.nodenum and "zz" not in tn.nodenum and "g" not in tn.nodenum
 
 
+def random_network_rows(tn):
+    """csv rows of a generated random network (component names r0, r1, ...; node labels of the generator)."""
+    t = tn.table()
+    label = {int(tn.nodenum[name]): name for name in tn.nodenum}
+    label[-1] = tn.ground
+    return [[f"r{k}", "R", repr(float(t.value[k])), label[int(t.a[k])], label[int(t.b[k])]] for k in range(len(t))]
+
+
+@pytest.mark.parametrize("locality", [None, 40])
+def test_random_network_numbering_matches_csv_path(locality, tmp_path):
+    """The sparse random-network generator numbers its rows exactly as the row-by-row Netlist
+    (the reference's first-appearance rule) numbers the same components read from a csv file."""
+    tn = gen.random_network(1500, degree=6, seed=3, locality=locality)
+    rows = random_network_rows(tn)
+    net = n.Netlist(write_csv(rows, tmp_path / "rn.csv"))
+    assert net.ground == tn.ground == "g"
+    assert dict(tn.nodenum) == net.nodenum and list(tn.nodenum) == list(net.nodenum)
+    t1, t2 = tn.table(), net.table()
+    for col in ("type", "value", "a", "b", "c", "d", "drv", "branch"):
+        assert np.array_equal(getattr(t1, col), getattr(t2, col)), col
+    assert t1.kcl == t2.kcl == 1499 and "1" in tn.nodenum and "g" not in tn.nodenum
+    # first-appearance numbering is not the node order: the network is irregular on purpose
+    ids = np.array([int(name[1:]) for name in list(tn.nodenum)[:200] if name.startswith("n")])
+    assert not np.all(np.diff(ids) > 0)
+
+
 def test_grid_nnz_formula():
     for N in (8, 33):
         t = gen.grid2d(N).table()

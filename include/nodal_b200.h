@@ -157,8 +157,8 @@ int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
  * [0] pairwise passes per level (2), [1] stop coarsening at this many rows (512), [2] Jacobi
  * damping (0.8), [3] coarse-correction scale (1.8), [4] max levels (30), [5] handshake rounds
  * (8), [6] largest coarsest level that is inverted explicitly (2048), [7] max_fill: coarsening stops
- * when a coarser operator would keep more than this fraction of the entries (0.7; graphs that
- * fill in instead of shrinking).
+ * when a coarser operator would hold more than this multiple of its parent's entries (1.2) or the
+ * operator complexity would pass 4 (graphs that fill in instead of shrinking).
  * nodal_amg_info: level count, rows / nnz per level (up to cap entries), setup time, whether the
  * coarsest level is solved exactly.  nodal_amg_fetch_level copies a level's aggregate map
  * (agg, n entries; not on the coarsest level) and/or CSR arrays to device buffers (NULL = skip).

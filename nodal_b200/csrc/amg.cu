@@ -44,7 +44,7 @@ struct nodal_amg {
     nodal_ctx* ctx = nullptr;
     int device = 0;
     int passes = 2, coarse = 512, maxlevels = 30, rounds = 8, direct_max = 2048;
-    double omega = 0.8, scale = 1.8, max_fill = 0.7;
+    double omega = 0.8, scale = 1.8, max_fill = 1.2, max_complexity = 4.0;
     std::vector<AmgLevel> lv;           // lv.back() is the coarsest level
     double* inv = nullptr;              // [nL x nL] inverse of the coarsest operator (or nullptr)
     double *p = nullptr, *q = nullptr, *r = nullptr, *z = nullptr;   // CG vectors
@@ -225,7 +225,13 @@ int build_hierarchy(nodal_amg* h, int32_t n, int64_t nnz, const int32_t* indptr,
         // stalled: hardly fewer rows, or hardly fewer entries (expander-like graphs fill in: every
         // coarse row couples to the union of its members' neighbourhoods and the hierarchy would
         // cost more per level than it gains)
-        if (rc != NODAL_OK || (double)A.n > 0.9 * (double)cur.n || (double)A.nnz > h->max_fill * (double)cur.nnz) {
+        // ... measured by the operator complexity the hierarchy would reach: sum of the levels'
+        // entries over the finest level's)
+        double total_nnz = (double)cur.nnz + (double)A.nnz;
+        for (const AmgLevel& P : h->lv) total_nnz += (double)P.nnz;
+        const bool too_dense = (double)A.nnz > h->max_fill * (double)cur.nnz ||
+                               total_nnz > h->max_complexity * (double)(h->lv.empty() ? cur.nnz : h->lv[0].nnz);
+        if (rc != NODAL_OK || (double)A.n > 0.9 * (double)cur.n || too_dense) {
             free_csr(ctx, A);       // error, or coarsening stalled: cur stays the coarsest level
             ctx_pool_free(ctx, comp);
             if (rc != NODAL_OK) {

@@ -412,7 +412,8 @@ struct Solver {
     int32_t* gather_need_dev = nullptr;   // [R] rows of every rank at the gathered level
     double* gather_stage = nullptr;       // NCCL path: R * gmax staging
     int32_t gmax = 0;
-    double omega = 0.8, scale = 1.8, max_fill = 0.7;
+    double omega = 0.8, scale = 1.8, max_fill = 1.2, max_complexity = 4.0;
+    double nnz_k_fine = 0.0, nnz_k_total = 0.0;      // entries (in units of 1024) of level 0 / of all levels so far
     int passes = 2, rounds = 8, maxlevels = 30;
     int64_t gather_below = 400000;
     double params_rep[8] = {0};
@@ -712,7 +713,9 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
         std::vector<int32_t> fine_k, coarse_k;
         NODAL_TRY(gather_counts(S, (int32_t)(nnz >> 10) + 1, fine_k));
         NODAL_TRY(gather_counts(S, (int32_t)(next->nnz >> 10) + 1, coarse_k));
-        if ((double)coarse_k[S.R] > S.max_fill * (double)fine_k[S.R]) {
+        S.nnz_k_total += (double)coarse_k[S.R];
+        if (S.nnz_k_fine == 0.0) { S.nnz_k_fine = (double)fine_k[S.R]; S.nnz_k_total += S.nnz_k_fine; }
+        if ((double)coarse_k[S.R] > S.max_fill * (double)fine_k[S.R] || S.nnz_k_total > S.max_complexity * S.nnz_k_fine) {
             amg_free_csr(ctx, *next);
             ctx_pool_free(ctx, comp);
             *stalled = true;

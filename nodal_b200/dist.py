@@ -98,14 +98,14 @@ class DistPCG:
 
     AMG_PARAMS = ("passes", "coarse", "omega", "scale", "maxlevels", "rounds", "direct_max", "gather_below", "max_fill")
 
-    def solve_amg(self, n_global, bounds, indptr, indices, data, rhs_local, rtol=1e-10, maxit=None, **params):
+    def solve_amg(self, n_global, bounds, indptr, indices, data, rhs_local, rtol=1e-10, maxit=None, x0=None, **params):
         """Row-partitioned AMG-preconditioned CG (csrc/dist_amg.cu)."""
         dev, torch = self.dev, self.dev.torch
         unknown = set(params) - set(self.AMG_PARAMS)
         if unknown:
             raise TypeError(f"unknown AMG parameter(s): {sorted(unknown)}")
         nloc = int(bounds[self.rank + 1] - bounds[self.rank])
-        x = dev.zeros(max(2, nloc), torch.float64)[:nloc]
+        x = dev.zeros(max(2, nloc), torch.float64)[:nloc] if x0 is None else x0.clone()
         b = np.ascontiguousarray(bounds, dtype=np.int32)
         arr = (C.c_double * 9)(*[float(params.get(k, 0.0)) for k in self.AMG_PARAMS])
         iters, relres = C.c_int32(0), C.c_double(0.0)

@@ -351,40 +351,73 @@ class Circuit:
             if first:
                 info["fallback_from_amg"] = first
             return x, info
+        if kind == "amg" and amg is None and self.options.get("precond", "auto") == "auto":
+            # "auto": which preconditioner pays depends on the graph, not on its size -- on a 4 M-node
+            # expander-like random network Jacobi-PCG needs 98 iterations (43 ms) and the AMG hierarchy
+            # 265 ms; on a banded random network of the same size it is 4 616 iterations (1.9 s)
+            # against 68 (156 ms); grids are the second kind.  A short Jacobi-PCG probe tells them
+            # apart: if 24 iterations gained two digits it will finish in ~100, otherwise its iterate
+            # is the initial guess of the AMG solve.
+            probe_its = int(self.options.get("auto_probe_iterations", 24))
+            if self.G.n >= self.options.get("auto_probe_min_rows", 50_000) and probe_its > 0:
+                x0, info0 = dev.pcg(self.G, rhs, rtol=rtol, maxit=probe_its, flags=self.options.get("pcg_flags", 0))
+                if info0["status"] == 0:
+                    info0["auto"] = "jacobi (converged inside the probe)"
+                    return x0, info0
+                if info0["status"] == 2 and info0["relres"] <= 1e-2:
+                    x, info = dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"), x0=x0,
+                                      flags=self.options.get("pcg_flags", 0))
+                    info["iterations"] += info0["iterations"]
+                    info["auto"] = f"jacobi (probe relres {info0['relres']:.1e})"
+                    if info["status"] == 0:
+                        return x, info
+                    x0 = x
+                elif info0["status"] != 2 or not np.isfinite(info0["relres"]):
+                    x0 = None                                  # breakdown in the probe: start AMG from zero
+                x, info = self._amg_solve(rhs, None, rtol, x0)
+                if x0 is not None:
+                    info["auto"] = f"amg (probe relres {info0['relres']:.1e})"
+                    info["iterations_probe"] = info0["iterations"]
+                return x, info
         if kind == "amg":
-            from . import _lib
-            try:
-                if amg is not None:
-                    x, info = amg.solve(rhs, rtol=rtol, maxit=self.options.get("maxit"))
-                elif self.G.n >= self.options.get("amg_graph_min_rows", 100_000):
-                    # large systems: the graph-captured form (csrc/dist_amg.cu with one rank):
-                    # one CUDA graph per iteration, no host round trip inside the iteration
-                    from . import dist as ndist
-                    g = self.G
-                    bounds = np.array([0, g.n], dtype=np.int32)
-                    x, info = ndist.single_solver(dev).solve_amg(
-                        g.n, bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol, maxit=self.options.get("maxit"),
-                        **(self.options.get("amg") or {}))
-                else:
-                    x, info = dev.amg_pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
-                                          **(self.options.get("amg") or {}))
-                if info["status"] == 0 or self.options.get("precond") == "amg":
-                    return x, info
-                first = f"amg_pcg status {info['status']} after {info['iterations']} iterations"
-            except _lib.NodalLibraryError as err:
-                if self.options.get("precond") == "amg":
-                    raise
-                first = str(err)
-            x, info = dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
-                              flags=self.options.get("pcg_flags", 0))
-            info["fallback_from_amg"] = first
-            return x, info
+            return self._amg_solve(rhs, amg, rtol, None)
         if kind == "pcg":
             return dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
                            flags=self.options.get("pcg_flags", 0))
         return dev.gmres(self.G, rhs, rtol=self.options.get("rtol", 1e-12),
                          restart=self.options.get("restart", 60),
                          maxit=self.options.get("maxit") or 20000)
+
+    def _amg_solve(self, rhs, amg, rtol, x0):
+        """AMG-preconditioned CG on one GPU; Jacobi-PCG retry unless precond="amg" was forced."""
+        dev = self._dev
+        from . import _lib
+        try:
+            if amg is not None:
+                x, info = amg.solve(rhs, rtol=rtol, maxit=self.options.get("maxit"), x0=x0)
+            elif self.G.n >= self.options.get("amg_graph_min_rows", 100_000):
+                # large systems: the graph-captured form (csrc/dist_amg.cu with one rank):
+                # one CUDA graph per iteration, no host round trip inside the iteration
+                from . import dist as ndist
+                g = self.G
+                bounds = np.array([0, g.n], dtype=np.int32)
+                x, info = ndist.single_solver(dev).solve_amg(
+                    g.n, bounds, g.indptr, g.indices, g.data, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                    x0=x0, **(self.options.get("amg") or {}))
+            else:
+                x, info = dev.amg_pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"), x0=x0,
+                                      **(self.options.get("amg") or {}))
+            if info["status"] == 0 or self.options.get("precond") == "amg":
+                return x, info
+            first = f"amg_pcg status {info['status']} after {info['iterations']} iterations"
+        except _lib.NodalLibraryError as err:
+            if self.options.get("precond") == "amg":
+                raise
+            first = str(err)
+        x, info = dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
+                          flags=self.options.get("pcg_flags", 0))
+        info["fallback_from_amg"] = first
+        return x, info
 
     def is_connected(self):
         """Every node reaches ground through component leads (the reference's is_connected,

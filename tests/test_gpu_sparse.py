@@ -239,8 +239,13 @@ def test_random_network_equivalent_resistance(device, locality):
     b = np.zeros(G.shape[0])
     b[tn.nodenum["1"]] = 1.0
     want = spla.spsolve(G, b)[tn.nodenum["1"]]
+    picked = None
     for precond in ("jacobi", "auto", "amg"):
-        r = n.equiv.equivalent_resistance(tn, "1", "g", sparse=True, precond=precond)
+        r = n.equiv.equivalent_resistance(tn, "1", "g", sparse=True, precond=precond, auto_probe_min_rows=1000)
         stats = n.equiv.equivalent_resistance.last_stats
         assert stats["status"] == 0 and stats["relres"] <= 1e-10, (precond, stats)
         assert r == pytest.approx(want, rel=1e-9), precond
+        if precond == "auto":
+            picked = stats.get("auto", "")
+    # the probe sends the expander-like graph to Jacobi and the banded one to AMG
+    assert picked.startswith("jacobi" if locality is None else "amg"), picked

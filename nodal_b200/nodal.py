@@ -384,9 +384,26 @@ class Circuit:
         if kind == "pcg":
             return dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
                            flags=self.options.get("pcg_flags", 0))
-        return dev.gmres(self.G, rhs, rtol=self.options.get("rtol", 1e-12),
-                         restart=self.options.get("restart", 60),
-                         maxit=self.options.get("maxit") or 20000)
+        x, info = dev.gmres(self.G, rhs, rtol=self.options.get("rtol", 1e-12),
+                            restart=self.options.get("restart", 60),
+                            maxit=self.options.get("maxit") or 20000)
+        # The reference's sparse path is a direct solve, exact for any non-singular MNA system; the
+        # diagonally preconditioned GMRES can stall on indefinite systems with many source /
+        # op-amp rows.  Rather than handing back an unconverged iterate, systems that fit the dense
+        # LU go through it; larger ones are reported (NaNs + warning in solve(), as for breakdown).
+        if info["status"] == 2 and self.options.get("gmres_fallback", True):
+            limit = int(self.options.get("dense_fallback_max_rows", 32768))
+            if self.G.n <= limit:
+                x, lu = dev.lu_solve(dev.csr_to_dense(self.G), rhs)
+                lu.update(solver="lu (after gmres did not converge)", gmres_iterations=info["iterations"],
+                          gmres_relres=info["relres"], relres=None)
+                if lu["status"] == 1:
+                    lu["status"] = 3            # singular: reported like a breakdown (NaNs + warning)
+                return x, lu
+            info["status"] = 3
+            info["note"] = (f"gmres did not converge (relres {info['relres']:.2e}) and the system has more than "
+                            f"{limit} rows (dense fallback limit)")
+        return x, info
 
     def _amg_solve(self, rhs, amg, rtol, x0):
         """AMG-preconditioned CG on one GPU; Jacobi-PCG retry unless precond="amg" was forced."""

@@ -293,3 +293,23 @@ def test_cli_end_to_end(device, tmp_path, capsys):
         with pytest.raises(SystemExit) as e:
             solver.main([path] + flags)
         assert e.value.code == 1
+
+
+def test_gmres_non_convergence_falls_back_to_dense_lu(device, tmp_path):
+    """The reference's -s path is a direct solve: an unconverged GMRES iterate must never be handed
+    back as the answer.  With an iteration budget GMRES cannot meet, the system goes through the
+    dense LU (it fits) and the result still matches the CPU solve to 1e-9 block-normwise."""
+    rows = orc.grid2d_rows(24)
+    rows += [["e1", "E", "5", "n3_3", "g"], ["d1", "VCVS", "2", "n20_7", "g", "n5_5", "n6_6"],
+             ["a1", "A", "1", "1", "g"]]
+    net = n.Netlist(write_csv(rows, tmp_path / "gs.csv"))
+    sol = n.Circuit(net, sparse=True, maxit=5).solve()
+    assert sol.stats["solver"].startswith("lu") and sol.stats["status"] == 0 and sol.stats["gmres_iterations"] == 5
+    onet, G, A, _, want = orc.solve_rows(rows, sparse=True, backend="dict")
+    assert block_err(sol.result, want, onet.kcl) < 1e-9
+    # above the dense limit the failure is reported (NaNs + warning), not hidden
+    import warnings
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        sol = n.Circuit(net, sparse=True, maxit=5, dense_fallback_max_rows=10).solve()
+    assert np.isnan(sol.result).all() and any("did not converge" in str(w.message) for w in caught)

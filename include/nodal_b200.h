@@ -199,6 +199,12 @@ int nodal_connected_components(nodal_ctx* ctx, int64_t ncomp, const int32_t* a, 
 int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double* rhs, double* x,
                    int32_t* info_h, void* stream);
 
+/* Measurement aid: the LU's DMMA trailing-update kernel alone, C[M x N] -= A[M x K] B[K x N] (row-major,
+ * even leading dimension ld), average ms per launch over `reps` launches (CUDA events on `stream`).
+ * Gives the FP64 tensor-pipe figure the dense path's roofline is quoted against. */
+int nodal_dgemm_sub_profile(nodal_ctx* ctx, double* C, const double* A, const double* B, int32_t M, int32_t N,
+                            int32_t K, int32_t ld, int32_t reps, double* ms_out, void* stream);
+
 /* Batched small systems sharing one topology: for copy s in [0, batch) stamp the
  * table with values[s*ncomp .. +ncomp) and solve the n x n system (n <= 32) with
  * partially pivoted LU in one thread.  x is batch x n row-major; info[s] = 0 or

@@ -538,3 +538,30 @@ extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double
     CUDA_TRY(cudaStreamSynchronize(st));
     return NODAL_OK;
 }
+
+// Measurement aid ("measure an FP64 GEMM-shaped peak on the box"): the
+// trailing-update kernel of the LU on its own, C[M x N] -= A[M x K] B[K x N] (row-major, leading
+// dimension ld, even), `reps` launches between two CUDA events on `stream`.  K = 128 is the shape
+// the LU uses (one panel); a large K shows what the DMMA pipe sustains when the C tile is
+// re-used, i.e. the denominator for the dense path's roofline.
+extern "C" int nodal_dgemm_sub_profile(nodal_ctx* ctx, double* Cm, const double* Am, const double* Bm, int32_t M,
+                                       int32_t N, int32_t K, int32_t ld, int32_t reps, double* ms_out, void* stream) {
+    if (!ctx || !Cm || !Am || !Bm || !ms_out || M < 1 || N < 1 || K < 1 || reps < 1 || (ld & 1)) return NODAL_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int rc = NODAL_OK;
+    for (int k = -2; k < reps && rc == NODAL_OK; ++k) {
+        if (k == 0) cudaEventRecord(e0, st);
+        rc = launch_gemm<4, true>(Cm, Am, Bm, M, N, K, ld, st);
+    }
+    cudaEventRecord(e1, st);
+    float ms = 0.f;
+    if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}

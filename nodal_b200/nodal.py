@@ -518,10 +518,9 @@ class Circuit:
 
         amg = None
         pairs = list(pairs)
-        graph_min = self.options.get("amg_graph_min_rows", 100_000)
-        # several right-hand sides share one hierarchy; a single large solve takes the
-        # graph-captured form instead (see _device_solve)
-        if self.sparse and run is None and self._sparse_solver() == "amg" and (len(pairs) > 1 or n < graph_min):
+        # several right-hand sides share one hierarchy; a single solve goes through _device_solve's
+        # own choice (auto probe, graph-captured form for large systems)
+        if self.sparse and run is None and self._sparse_solver() == "amg" and len(pairs) > 1:
             from . import _lib
             try:
                 amg = dev.amg(self.G, **(self.options.get("amg") or {}))

@@ -467,12 +467,14 @@ extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double
         CUDA_TRY(cudaFuncSetAttribute(lu_apply_pivots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
 
-    // Right-looking LU with one panel of look-ahead: as soon as step k has updated the NEXT panel's
-    // columns, panel k+1 is factored on a second (high-priority) stream while the main stream
-    // applies step k to the remaining columns -- the panel (one grid sync per column, a quarter of
-    // the run time at n = 16 384) hides behind the DMMA update.  NODAL_LU_NO_LOOKAHEAD=1 runs the
-    // strictly sequential schedule.
-    const bool lookahead = getenv("NODAL_LU_NO_LOOKAHEAD") == nullptr && n > 2 * LU_NB;
+    // Right-looking LU.  Opt-in (NODAL_LU_LOOKAHEAD=1): one panel of look-ahead -- as soon as step k
+    // has updated the NEXT panel's columns, panel k+1 is launched on a second (high-priority)
+    // stream while the main stream applies step k to the remaining columns.  Measured on B200
+    // (round 2): no gain, 261 vs 252 ms at n = 16 384 -- the cooperative panel grid (one CTA per SM,
+    // ~117 KB of shared memory each) does not become co-resident next to the DMMA update's two
+    // 108 KB CTAs per SM, so the two kernels still run back to back and the split update only adds
+    // launches.  Kept off by default; the schedule is here for a panel that needs fewer SMs.
+    const bool lookahead = getenv("NODAL_LU_LOOKAHEAD") != nullptr && n > 2 * LU_NB;
     cudaStream_t sp = st;
     cudaEvent_t ev_panel = nullptr, ev_ready = nullptr;
     if (lookahead) {

@@ -116,6 +116,67 @@ int amg_transpose_pattern(nodal_ctx* ctx, int32_t n, const int32_t* agg, int32_t
     return NODAL_OK;
 }
 
+int amg_members(nodal_ctx* ctx, int32_t n, const int32_t* agg, int32_t nc, int32_t** pt_ptr_out,
+                int32_t** pt_idx_out, cudaStream_t st) {
+    AmgScratch<u32> cnt(ctx, (size_t)nc + 1), cursor(ctx, (size_t)nc + 1);
+    AmgScratch<int32_t> pp(ctx, (size_t)nc + 1), pi(ctx, (size_t)std::max(n, 1));
+    if (!cnt.ptr || !cursor.ptr || !pp.ptr || !pi.ptr) return NODAL_CUDA_ERROR;
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(u32) * ((size_t)nc + 1), st));
+    CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(u32) * ((size_t)nc + 1), st));
+    const int grid = amg_rows_grid(ctx, n);
+    amg_count_members_kernel<<<grid, AT, 0, st>>>(n, agg, cnt);
+    KERNEL_CHECK();
+    NODAL_TRY(ctx_reserve(ctx, scan_scratch_bytes((int64_t)nc + 1) + 4096));
+    NODAL_TRY(scan_exclusive_u32(ctx, cnt, reinterpret_cast<u32*>(pp.ptr), (int64_t)nc + 1, nullptr, st));
+    amg_place_members_kernel<<<grid, AT, 0, st>>>(n, agg, pp, cursor, pi);
+    KERNEL_CHECK();
+    amg_sort_members_kernel<<<amg_rows_grid(ctx, nc), AT, 0, st>>>(nc, pp, pi);
+    KERNEL_CHECK();
+    *pt_ptr_out = pp.keep();
+    *pt_idx_out = pi.keep();
+    return NODAL_OK;
+}
+
+int amg_galerkin_merge(nodal_ctx* ctx, const AmgCsr& A, const int32_t* pt_ptr, const int32_t* pt_idx, int32_t nc,
+                       const int32_t* label, int32_t ncol_limit, AmgCsr* out, cudaStream_t st) {
+    if (A.nnz >= ((int64_t)1 << 32) - 1) return NODAL_BAD_ARG;
+    AmgScratch<u32> bound(ctx, (size_t)nc + 1), kept(ctx, (size_t)nc + 1);
+    AmgScratch<int32_t> tmp_cols(ctx, (size_t)std::max<int64_t>(A.nnz, 1)), ip(ctx, (size_t)nc + 1);
+    AmgScratch<double> tmp_vals(ctx, (size_t)std::max<int64_t>(A.nnz, 1));
+    if (!bound.ptr || !kept.ptr || !tmp_cols.ptr || !tmp_vals.ptr || !ip.ptr) return NODAL_CUDA_ERROR;
+    const int grid = amg_rows_grid(ctx, nc);
+    CUDA_TRY(cudaMemsetAsync(bound.ptr + nc, 0, sizeof(u32), st));
+    CUDA_TRY(cudaMemsetAsync(kept.ptr + nc, 0, sizeof(u32), st));
+    amg_merge_bound_kernel<<<grid, AT, 0, st>>>(nc, pt_ptr, pt_idx, A.indptr, bound);
+    KERNEL_CHECK();
+    NODAL_TRY(ctx_reserve(ctx, scan_scratch_bytes((int64_t)nc + 1) + 4096));
+    u32* total = carve<u32>(ctx, 16);
+    if (!total) return NODAL_CUDA_ERROR;
+    const size_t mark = ctx->arena_used;
+    NODAL_TRY(scan_exclusive_u32(ctx, bound, bound, (int64_t)nc + 1, nullptr, st));
+    ctx->arena_used = mark;
+    amg_merge_rows_kernel<<<grid, AT, 0, st>>>(nc, pt_ptr, pt_idx, A.indptr, A.indices, A.data, label, ncol_limit,
+                                               bound, tmp_cols, tmp_vals, kept);
+    KERNEL_CHECK();
+    NODAL_TRY(scan_exclusive_u32(ctx, kept, reinterpret_cast<u32*>(ip.ptr), (int64_t)nc + 1, total, st));
+    u32* total_h = reinterpret_cast<u32*>(ctx->pinned);
+    CUDA_TRY(cudaMemcpyAsync(total_h, total, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t nnzc = total_h[0];
+    AmgScratch<int32_t> ix(ctx, (size_t)std::max<int64_t>(nnzc, 1));
+    AmgScratch<double> dv(ctx, (size_t)std::max<int64_t>(nnzc, 1));
+    if (!ix.ptr || !dv.ptr) return NODAL_CUDA_ERROR;
+    amg_merge_compact_kernel<<<grid, AT, 0, st>>>(nc, bound, ip, tmp_cols, tmp_vals, ix, dv);
+    KERNEL_CHECK();
+    out->n = nc;
+    out->nnz = nnzc;
+    out->indptr = ip.keep();
+    out->indices = ix.keep();
+    out->data = dv.keep();
+    out->owned = true;
+    return NODAL_OK;
+}
+
 namespace {
 
 int rows_grid(const nodal_ctx* ctx, int64_t work) { return amg_rows_grid(ctx, work); }
@@ -132,8 +193,23 @@ int aggregate(nodal_amg* h, const Csr& A, int32_t** agg_out, int32_t* nc_out, cu
 }
 
 // Ac = P^T A P for the piecewise-constant P of `agg`.
+bool sorted_galerkin() {
+    static const bool on = getenv("NODAL_AMG_SORT_GALERKIN") != nullptr;
+    return on;
+}
+
 int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* out, cudaStream_t st) {
     nodal_ctx* ctx = h->ctx;
+    if (!sorted_galerkin()) {
+        // sort-free: members of every aggregate, then one thread merges the member rows of its
+        // coarse row (same summation order as the sort-based product below: bit-identical)
+        int32_t *pp = nullptr, *pi = nullptr;
+        NODAL_TRY(amg_members(ctx, A.n, agg, nc, &pp, &pi, st));
+        const int rc = amg_galerkin_merge(ctx, A, pp, pi, nc, agg, 0x7fffffff, out, st);
+        ctx_pool_free(ctx, pp);
+        ctx_pool_free(ctx, pi);
+        return rc;
+    }
     Scratch<u64> keys(ctx, A.nnz);
     Scratch<double> vals(ctx, A.nnz), rhs(ctx, (size_t)nc + 1);
     if (!keys.ptr || !vals.ptr || !rhs.ptr) return NODAL_CUDA_ERROR;
@@ -158,6 +234,7 @@ int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* ou
 }
 
 int transpose_pattern(nodal_amg* h, AmgLevel& L, cudaStream_t st) {
+    if (!sorted_galerkin()) return amg_members(h->ctx, L.n, L.agg, L.nc, &L.pt_ptr, &L.pt_idx, st);
     return amg_transpose_pattern(h->ctx, L.n, L.agg, &L.pt_ptr, &L.pt_idx, st);
 }
 

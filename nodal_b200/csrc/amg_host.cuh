@@ -62,3 +62,12 @@ int amg_aggregate(nodal_ctx* ctx, int rounds, const AmgCsr& A, int32_t nown, int
 // pt_ptr[n + 1] / pt_idx[n] owned by the caller.
 int amg_transpose_pattern(nodal_ctx* ctx, int32_t n, const int32_t* agg, int32_t** pt_ptr,
                           int32_t** pt_idx, cudaStream_t st);
+
+// The same without a sort (count / scan / place / per-aggregate ordering): nc aggregates.
+int amg_members(nodal_ctx* ctx, int32_t n, const int32_t* agg, int32_t nc, int32_t** pt_ptr, int32_t** pt_idx,
+                cudaStream_t st);
+// Rows [0, nc) of P^T A P by merging the member rows of every coarse row (amg_merge_core.cuh):
+// A's rows are the fine rows the members refer to, `label[col]` is the coarse column of a fine
+// column, columns >= ncol_limit are skipped.  Bit-identical to the sort + in-order sum it replaces.
+int amg_galerkin_merge(nodal_ctx* ctx, const AmgCsr& A, const int32_t* pt_ptr, const int32_t* pt_idx, int32_t nc,
+                       const int32_t* label, int32_t ncol_limit, AmgCsr* out, cudaStream_t st);

@@ -3,6 +3,7 @@
 // See amg.cu for the algorithm notes.
 #pragma once
 #include "amg_core.cuh"
+#include "amg_merge_core.cuh"
 #include "sparse.cuh"
 
 constexpr int AT = 256;
@@ -231,3 +232,64 @@ apcg_direction_kernel(int32_t n, const double* __restrict__ part_rz, int nrz,
     if (blockIdx.x == 0 && threadIdx.x == 0) rz_new[0] = rzn;
 }
 
+
+// ------------------------------------------------------------------ sort-free setup kernels
+// Members of every aggregate: count, scan, place (arrival order), then every aggregate sorts its
+// own few members -- the result (rows in increasing order) does not depend on the atomics' order.
+static __global__ void __launch_bounds__(AT)
+amg_count_members_kernel(int32_t n, const int32_t* __restrict__ agg, u32* __restrict__ cnt) {
+    ROW_LOOP(i, n) atomicAdd(&cnt[agg[i]], 1u);
+}
+
+static __global__ void __launch_bounds__(AT)
+amg_place_members_kernel(int32_t n, const int32_t* __restrict__ agg, const int32_t* __restrict__ pt_ptr,
+                         u32* __restrict__ cursor, int32_t* __restrict__ pt_idx) {
+    ROW_LOOP(i, n) {
+        const int32_t a = agg[i];
+        pt_idx[pt_ptr[a] + (int32_t)atomicAdd(&cursor[a], 1u)] = (int32_t)i;
+    }
+}
+
+static __global__ void __launch_bounds__(AT)
+amg_sort_members_kernel(int32_t nc, const int32_t* __restrict__ pt_ptr, int32_t* __restrict__ pt_idx) {
+    ROW_LOOP(I, nc) {
+        const int32_t b = pt_ptr[I], e = pt_ptr[I + 1];
+        for (int32_t p = b + 1; p < e; ++p) {
+            const int32_t v = pt_idx[p];
+            int32_t q = p;
+            while (q > b && pt_idx[q - 1] > v) { pt_idx[q] = pt_idx[q - 1]; --q; }
+            pt_idx[q] = v;
+        }
+    }
+}
+
+// Galerkin product by merging (amg_merge_core.cuh): upper bounds, rows into their slices, compaction.
+static __global__ void __launch_bounds__(AT)
+amg_merge_bound_kernel(int32_t nc, const int32_t* __restrict__ pt_ptr, const int32_t* __restrict__ pt_idx,
+                       const int32_t* __restrict__ indptr, u32* __restrict__ bound) {
+    ROW_LOOP(I, nc) bound[I] = (u32)amg_merge_bound((int32_t)I, pt_ptr, pt_idx, indptr);
+}
+
+static __global__ void __launch_bounds__(AT)
+amg_merge_rows_kernel(int32_t nc, const int32_t* __restrict__ pt_ptr, const int32_t* __restrict__ pt_idx,
+                      const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                      const double* __restrict__ data, const int32_t* __restrict__ label, int32_t ncol_limit,
+                      const u32* __restrict__ off, int32_t* tmp_cols, double* tmp_vals, u32* __restrict__ kept) {
+    ROW_LOOP(I, nc)
+        kept[I] = (u32)amg_merge_row((int32_t)I, pt_ptr, pt_idx, indptr, indices, data, label, tmp_cols + off[I],
+                                     tmp_vals + off[I], ncol_limit);
+}
+
+static __global__ void __launch_bounds__(AT)
+amg_merge_compact_kernel(int32_t nc, const u32* __restrict__ off, const int32_t* __restrict__ out_ptr,
+                         const int32_t* __restrict__ tmp_cols, const double* __restrict__ tmp_vals,
+                         int32_t* __restrict__ out_cols, double* __restrict__ out_vals) {
+    ROW_LOOP(I, nc) {
+        const int32_t b = out_ptr[I], cnt = out_ptr[I + 1] - b;
+        const u32 src = off[I];
+        for (int32_t k = 0; k < cnt; ++k) {
+            out_cols[b + k] = tmp_cols[src + k];
+            out_vals[b + k] = tmp_vals[src + k];
+        }
+    }
+}

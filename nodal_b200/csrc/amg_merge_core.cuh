@@ -1,13 +1,15 @@
-// PROTOTYPE (host-verified, not yet part of libnodal_b200.so): Galerkin product P^T A P for a
-// piecewise-constant P without the global radix sort csrc/amg.cu uses today (29 of its 51 ms of
-// setup at 16.7 M rows).  One thread owns one coarse row: it walks the fine rows of its aggregate
+// Galerkin product P^T A P for a piecewise-constant P without a global sort (round 1 relabelled
+// every entry and ran the assembly's radix sort + segmented sum: 29 of 51 ms of the AMG setup at
+// 16.7 M rows).  One thread owns one coarse row: it walks the fine rows of its aggregate
 // in increasing row order, every row in CSR order, maps the columns through `agg`, and keeps a
 // small list sorted by coarse column in its slice of the output (insertion from the back -- the
 // columns arrive nearly sorted).  Duplicates are added in arrival order, which is the order the
 // stable sort + in-order segmented sum produces, so the coarse values are bit-identical to the
 // current path and to tests/amg_mirror.galerkin.  Exact zeros are dropped at the end (DOK
-// semantics of csr.cu).  Written __host__ __device__ so that tests/test_amg_merge_host.py can
-// check it on the CPU before it is wired into amg.cu.
+// semantics of csr.cu).  Written __host__ __device__: tests/test_amg_merge_host.py compiles it
+// for the CPU and checks it against the numpy statement; amg_host.cuh runs it on the device.
+// Row-partitioned setup: `label` maps a LOCAL column (owned or halo) to its coarse column id and
+// columns >= ncol_limit are skipped (the local-local block the second pairwise pass looks at).
 #pragma once
 #include <stdint.h>
 
@@ -32,12 +34,14 @@ AMG_MERGE_HD int32_t amg_merge_bound(int32_t I, const int32_t* pt_ptr, const int
 // number of entries kept.
 AMG_MERGE_HD int32_t amg_merge_row(int32_t I, const int32_t* pt_ptr, const int32_t* pt_idx,
                                    const int32_t* indptr, const int32_t* indices, const double* data,
-                                   const int32_t* agg, int32_t* out_cols, double* out_vals) {
+                                   const int32_t* label, int32_t* out_cols, double* out_vals,
+                                   int32_t ncol_limit = 0x7fffffff) {
     int32_t len = 0;
     for (int32_t q = pt_ptr[I]; q < pt_ptr[I + 1]; ++q) {
         const int32_t i = pt_idx[q];
         for (int32_t p = indptr[i]; p < indptr[i + 1]; ++p) {
-            const int32_t c = agg[indices[p]];
+            if (indices[p] >= ncol_limit) continue;
+            const int32_t c = label[indices[p]];
             const double v = data[p];
             int32_t pos = len;                       // first position whose column is >= c, from the back
             while (pos > 0 && out_cols[pos - 1] >= c) --pos;

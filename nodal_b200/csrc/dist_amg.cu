@@ -135,6 +135,10 @@ da_relabel_global_kernel(int32_t n, const int32_t* __restrict__ indptr, const in
     }
 }
 __global__ void __launch_bounds__(DA)
+da_labels_to_i32_kernel(int32_t n, const double* __restrict__ lab, int32_t* __restrict__ out) {
+    GRID_LOOP(i, n) out[i] = (int32_t)lab[i];
+}
+__global__ void __launch_bounds__(DA)
 da_slice_indptr_kernel(int32_t nloc, const int32_t* __restrict__ src, int32_t* __restrict__ dst) {
     const int32_t first = src[0];
     GRID_LOOP(i, (int64_t)nloc + 1) dst[i] = src[i] - first;
@@ -414,6 +418,7 @@ struct Solver {
     int32_t gmax = 0;
     double omega = 0.8, scale = 1.8, max_fill = 1.2, max_complexity = 4.0;
     double nnz_k_fine = 0.0, nnz_k_total = 0.0;      // entries (in units of 1024) of level 0 / of all levels so far
+    bool sorted_galerkin = getenv("NODAL_AMG_SORT_GALERKIN") != nullptr;   // round-2 first version: sort-based products
     int passes = 2, rounds = 8, maxlevels = 30;
     int64_t gather_below = 400000;
     double params_rep[8] = {0};
@@ -660,9 +665,23 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
             amg_compose_kernel<<<amg_rows_grid(ctx, nloc), AT, 0, st>>>(nloc, comp, agg);
             KERNEL_CHECK();
         }
-        if (pass + 1 < S.passes) {
+        if (pass + 1 < S.passes && !S.sorted_galerkin) {
             // operator the next pass aggregates: the local-local block of P^T A P (couplings to
-            // other ranks are invisible to the matching, see amg_core.cuh)
+            // other ranks are invisible to the matching, see amg_core.cuh), merged per coarse row
+            int32_t *pp = nullptr, *pi = nullptr;
+            NODAL_TRY(amg_members(ctx, cur.n, agg, nc, &pp, &pi, st));
+            AmgCsr nxt;
+            const int rc = amg_galerkin_merge(ctx, cur, pp, pi, nc, agg, cur_own, &nxt, st);
+            ctx_pool_free(ctx, pp);
+            ctx_pool_free(ctx, pi);
+            NODAL_TRY(rc);
+            if (cur.owned) amg_free_csr(ctx, cur);
+            cur = nxt;
+            std::vector<int32_t> ib;
+            NODAL_TRY(gather_counts(S, nc, ib));
+            cur_own = nc;
+            cur_base = ib[S.me];
+        } else if (pass + 1 < S.passes) {
             AmgScratch<u64> keys(ctx, (size_t)std::max<int64_t>(cur.nnz, 1));
             AmgScratch<double> vals(ctx, (size_t)std::max<int64_t>(cur.nnz, 1));
             if (!keys.ptr || !vals.ptr) return NODAL_CUDA_ERROR;
@@ -698,7 +717,20 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
     da_labels_kernel<<<amg_rows_grid(ctx, nloc), DA, 0, st>>>(nloc, comp, (*next_bounds)[S.me], lab);
     KERNEL_CHECK();
     NODAL_TRY(exchange_nccl(S, L.halo, lab, st));
-    {
+    bool have_members = false;
+    if (!S.sorted_galerkin) {
+        // members of the composed aggregates (also the restriction pattern), then one thread merges
+        // the member rows of its coarse row with the global coarse column ids
+        AmgScratch<int32_t> lab32(ctx, (size_t)L.halo.ext_len + 2);
+        if (!lab32.ptr) return NODAL_CUDA_ERROR;
+        da_labels_to_i32_kernel<<<amg_rows_grid(ctx, L.halo.ext_len), DA, 0, st>>>(L.halo.ext_len, lab, lab32);
+        KERNEL_CHECK();
+        NODAL_TRY(amg_members(ctx, nloc, comp, ncur, &L.pt_ptr, &L.pt_idx, st));
+        S.owned.push_back(L.pt_ptr);
+        S.owned.push_back(L.pt_idx);
+        have_members = true;
+        NODAL_TRY(amg_galerkin_merge(ctx, loc, L.pt_ptr, L.pt_idx, ncur, lab32, 0x7fffffff, next, st));
+    } else {
         AmgScratch<u64> keys(ctx, (size_t)std::max<int64_t>(nnz, 1));
         AmgScratch<double> vals(ctx, (size_t)std::max<int64_t>(nnz, 1));
         if (!keys.ptr || !vals.ptr) return NODAL_CUDA_ERROR;
@@ -725,9 +757,11 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
     L.agg = comp;
     S.owned.push_back(comp);
     L.nc = ncur;
-    NODAL_TRY(amg_transpose_pattern(ctx, nloc, comp, &L.pt_ptr, &L.pt_idx, st));
-    S.owned.push_back(L.pt_ptr);
-    S.owned.push_back(L.pt_idx);
+    if (!have_members) {
+        NODAL_TRY(amg_transpose_pattern(ctx, nloc, comp, &L.pt_ptr, &L.pt_idx, st));
+        S.owned.push_back(L.pt_ptr);
+        S.owned.push_back(L.pt_idx);
+    }
     return NODAL_OK;
 }
 

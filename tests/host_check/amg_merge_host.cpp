@@ -1,10 +1,10 @@
-// TEST-ONLY host driver of the merge-based Galerkin prototype (amg_merge_core.h): the schedule a
+// TEST-ONLY host driver of the merge-based Galerkin product (nodal_b200/csrc/amg_merge_core.cuh): the schedule a
 // CUDA version would run -- bounds, exclusive scan, one "thread" per coarse row, compaction.
 #include <stdint.h>
 
 #include <vector>
 
-#include "amg_merge_core.h"
+#include "../../nodal_b200/csrc/amg_merge_core.cuh"
 
 // out_indptr[nc + 1]; out_indices / out_data sized for the upper bound (sum of fine nnz).
 extern "C" int64_t amg_galerkin_merge_host(int32_t nc, const int32_t* pt_ptr, const int32_t* pt_idx,

@@ -1,5 +1,5 @@
-"""CPU check of the merge-based Galerkin prototype (tests/host_check/amg_merge_core.h, the planned
-replacement of the sort-based coarse-operator build in csrc/amg.cu): bit-identical to the numpy
+"""CPU check of the merge-based Galerkin product (nodal_b200/csrc/amg_merge_core.cuh, what csrc/amg.cu
+and csrc/dist_amg.cu build their coarse operators with): bit-identical to the numpy
 statement amg_mirror.galerkin, i.e. to what the shipped sort + in-order segmented sum produces."""
 import ctypes as C
 import os
@@ -22,7 +22,8 @@ def lib():
         out = os.path.join(HERE, "host_check", "_build")
         os.makedirs(out, exist_ok=True)
         so = os.path.join(out, "libamg_merge_host.so")
-        srcs = [os.path.join(HERE, "host_check", f) for f in ("amg_merge_host.cpp", "amg_merge_core.h")]
+        srcs = [os.path.join(HERE, "host_check", "amg_merge_host.cpp"),
+                os.path.join(HERE, "..", "nodal_b200", "csrc", "amg_merge_core.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", srcs[0], "-o", so])
         _lib = C.CDLL(so)

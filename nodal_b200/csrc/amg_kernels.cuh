@@ -275,9 +275,22 @@ amg_merge_rows_kernel(int32_t nc, const int32_t* __restrict__ pt_ptr, const int3
                       const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                       const double* __restrict__ data, const int32_t* __restrict__ label, int32_t ncol_limit,
                       const u32* __restrict__ off, int32_t* tmp_cols, double* tmp_vals, u32* __restrict__ kept) {
-    ROW_LOOP(I, nc)
-        kept[I] = (u32)amg_merge_row((int32_t)I, pt_ptr, pt_idx, indptr, indices, data, label, tmp_cols + off[I],
-                                     tmp_vals + off[I], ncol_limit);
+    // Short rows (the common case: 2 - 3 member rows of 5 - 9 entries) are merged in a thread-local
+    // list and written out once; the insertion's read-backs otherwise go to the global slice.
+    constexpr int LOCAL = 32;
+    ROW_LOOP(I, nc) {
+        const u32 o = off[I];
+        if (off[I + 1] - o <= (u32)LOCAL) {
+            int32_t lc[LOCAL];
+            double lv[LOCAL];
+            const int32_t k = amg_merge_row((int32_t)I, pt_ptr, pt_idx, indptr, indices, data, label, lc, lv, ncol_limit);
+            for (int32_t e = 0; e < k; ++e) { tmp_cols[o + e] = lc[e]; tmp_vals[o + e] = lv[e]; }
+            kept[I] = (u32)k;
+        } else {
+            kept[I] = (u32)amg_merge_row((int32_t)I, pt_ptr, pt_idx, indptr, indices, data, label, tmp_cols + o,
+                                         tmp_vals + o, ncol_limit);
+        }
+    }
 }
 
 static __global__ void __launch_bounds__(AT)

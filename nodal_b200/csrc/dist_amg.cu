@@ -230,7 +230,27 @@ acg_vector_kernel(PcgDev* __restrict__ dev, int32_t n, double* __restrict__ cur,
     }
     if (conv || bad) return;
     double lrr = 0.0;
-    GRID_LOOP(i, n) {
+    // ten streams (p, s, r, x read + written, u, w read): 16-byte accesses
+    const int64_t n2 = n >> 1;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* s2 = reinterpret_cast<double2*>(s);
+    const double2* u2 = reinterpret_cast<const double2*>(u);
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    GRID_LOOP(i, n2) {
+        double2 pv = p2[i], sv = s2[i], rv = r2[i], xv = x2[i];
+        const double2 uv = u2[i], wv = w2[i];
+        pv.x = fma(beta, pv.x, uv.x);   pv.y = fma(beta, pv.y, uv.y);
+        sv.x = fma(beta, sv.x, wv.x);   sv.y = fma(beta, sv.y, wv.y);
+        rv.x = fma(-alpha, sv.x, rv.x); rv.y = fma(-alpha, sv.y, rv.y);
+        xv.x = fma(alpha, pv.x, xv.x);  xv.y = fma(alpha, pv.y, xv.y);
+        p2[i] = pv; s2[i] = sv; r2[i] = rv; x2[i] = xv;
+        lrr = fma(rv.x, rv.x, lrr);
+        lrr = fma(rv.y, rv.y, lrr);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
         const double pv = fma(beta, p[i], u[i]);
         const double sv = fma(beta, s[i], w[i]);
         const double rv = fma(-alpha, sv, r[i]);

@@ -71,6 +71,28 @@ def main():
             runner.pcg.close()
             if rank == 0:
                 print(json.dumps(msg), flush=True)
+    # ---- the nodal surface under torchrun: Circuit(..., distributed=True) and equivalent_resistance
+    import nodal_b200 as n
+    import nodal_b200.equiv
+    for N in [s for s in sizes if s <= 400][:2]:
+        tn = gen.grid2d(N)
+        for precond in ("auto", "jacobi"):
+            r = n.equiv.equivalent_resistance(tn, "1", "g", sparse=True, distributed=True, precond=precond)
+            stats = n.equiv.equivalent_resistance.last_stats
+            good = stats["status"] == 0 and (N not in GOLD or abs(r - GOLD[N]) / GOLD[N] < 1e-9)
+            ok &= good
+            if rank == 0:
+                print(json.dumps(dict(surface="equivalent_resistance(distributed=True)", N=N, precond=precond, R=r,
+                                      solver=stats["solver"], iterations=stats["iterations"], ok=bool(good))), flush=True)
+        probe = copy.deepcopy(tn)
+        probe.process_component(["a1", "A", "1", "1", "g"])
+        sol = n.Circuit(probe, sparse=True, distributed=True).solve()        # whole vector on every rank
+        ref = n.Circuit(probe, sparse=True, precond="jacobi").solve()        # this rank's own single-GPU solve
+        err = float(np.max(np.abs(sol.result - ref.result)) / np.max(np.abs(ref.result)))
+        ok &= err < 1e-8 and len(sol.result) == probe.table().n
+        if rank == 0:
+            print(json.dumps(dict(surface="Circuit(distributed=True).solve()", N=N, solver=sol.stats["solver"],
+                                  max_rel_diff_vs_single_gpu=err)), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -155,7 +155,7 @@ class ClockSampler:
         self.lines, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -312,11 +312,12 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_ms /= args.steps
     e2e = {"value": n_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s",
-           "h2d_bytes_per_step": int(Device.uploaded_bytes(net.table())) * world, "d2h_bytes_per_step": 16 * world,
+           "h2d_bytes_per_step": int(Device.uploaded_bytes(net.table())), "d2h_bytes_per_step": 16 * world,
            "ms_per_step": e2e_ms, "R": r_e2e, "solver": e2e_stats.get("solver"),
            "api": "nodal_b200.equiv.equivalent_resistance(netlist, '1', 'g', sparse=True" +
                   (", distributed=True" if world > 1 else "") + ") on a host TableNetlist (pinned columns) on every "
-                  "rank: whole table up, the two probe potentials down (bytes summed over ranks)"}
+                  "rank: every rank uploads its 1/N share of the table (the rows a rank stamps reach it over NVLink), "
+                  "the two probe potentials come down (bytes summed over ranks)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -300,7 +300,7 @@ class Circuit:
         runner = ndist.GridRunner(dev, table, 0, rank, world, rtol=self.options.get("rtol", 1e-10),
                                   precond="jacobi" if self.options.get("precond") == "jacobi" else "amg",
                                   amg=self.options.get("amg"), solver=ndist.shared_solver(dev, rank, world))
-        indptr, indices, data, rhs = runner.assemble(dev.upload_table(table))
+        indptr, indices, data, rhs = runner.assemble_from_host()
         self._dist = runner
         return ndist.LocalRows(table.n, runner.bounds, rank, indptr, indices, data), rhs
 

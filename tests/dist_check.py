@@ -93,6 +93,19 @@ def main():
         if rank == 0:
             print(json.dumps(dict(surface="Circuit(distributed=True).solve()", N=N, solver=sol.stats["solver"],
                                   max_rel_diff_vs_single_gpu=err)), flush=True)
+    # ---- the host path (share upload + device selection + all_to_all) builds the same rows as the
+    # selection from the full resident table
+    for N in sizes[:2]:
+        net = copy.deepcopy(gen.grid2d(N))
+        net.process_component(["a1", "A", "1", "1", "g"])
+        table = net.table()
+        runner = ndist.GridRunner(dev, table, net.nodenum["1"], rank, world, solver=ndist.shared_solver(dev, rank, world))
+        a = runner.assemble(dev.upload_table(table))
+        b = runner.assemble_from_host()
+        same = all(torch.equal(u, v) for u, v in zip(a, b))
+        ok &= same
+        if rank == 0:
+            print(json.dumps(dict(check="assemble_from_host == assemble(resident table)", N=N, bit_identical=bool(same))), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -291,17 +291,19 @@ onesweep_bases_kernel(u32* __restrict__ ghist) {
     row[threadIdx.x] = ex;
 }
 
-// 256 threads x 8 keys per tile of 2048 at 4 CTAs / SM.  History (16.8 M-row grid, 134 M pairs,
-// ncu): 256 x 16 keys, 128 registers, 2 CTAs / SM: 1.60 ms per pass; 512 x 8, 2 CTAs / SM: 1.45 ms;
-// + windowed look-back: 1.34 ms = 3.2 TB/s with DRAM traffic equal to the algorithmic 4.3 GB --
-// warps stalled at the tile's barriers and on the loads in front of them (half of the issue
-// slots each), so more, smaller, independent CTAs per SM decorrelate the phases.
-constexpr int OS_THREADS = 256;
+// 512 threads x 8 keys per tile of 4096 at 2 CTAs / SM (32 resident warps).  History on the
+// 16.8 M-row grid (134 M pairs, ncu, per pass): 256 x 16 keys at 128 registers, 2 CTAs / SM: 1.60 ms;
+// 512 x 8 at 64 registers: 1.45 ms; + windowed look-back: 1.34 ms = 3.2 TB/s with DRAM traffic equal
+// to the algorithmic 4.35 GB (round 1's three-kernel pass: 3.5 ms).  256 x 8 tiles at 4 CTAs / SM were
+// slower again (1.47 ms): warps wait at the tile's barriers and on the loads in front of them in
+// equal parts, so the next step is overlapping a tile's loads with the previous tile's scatter
+// inside one CTA, not more CTAs.
+constexpr int OS_THREADS = 512;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_IPT = 8;
 constexpr int OS_TILE = OS_THREADS * OS_IPT;
 constexpr int OS_LOOK = 8;
-constexpr int OS_CTAS_PER_SM = 4;
+constexpr int OS_CTAS_PER_SM = 2;
 
 __global__ void __launch_bounds__(OS_THREADS, OS_CTAS_PER_SM)
 onesweep_pass_kernel(const u64* __restrict__ keys_in, const u64* __restrict__ vals_in,

@@ -200,7 +200,7 @@ bool sorted_galerkin() {
 
 int galerkin(nodal_amg* h, const Csr& A, const int32_t* agg, int32_t nc, Csr* out, cudaStream_t st) {
     nodal_ctx* ctx = h->ctx;
-    if (!sorted_galerkin()) {
+    if (!sorted_galerkin() && amg_merge_pays(A.nnz, nc)) {
         // sort-free: members of every aggregate, then one thread merges the member rows of its
         // coarse row (same summation order as the sort-based product below: bit-identical)
         int32_t *pp = nullptr, *pi = nullptr;

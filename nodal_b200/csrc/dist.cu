@@ -1084,12 +1084,20 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
         A.n = nloc; A.nnz = nnz; A.indptr = indptr; A.indices = lcols; A.data = data;
         const double mean = (double)nnz / nloc;
         A.tpr = mean <= 2.5 ? 2 : mean <= 6.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
-        const bool use_sell = (double)sell->padded <= 1.5 * (double)nnz + 1024.0;
-        if (use_sell) A.sell = sell;
-        else if (unit) {
-            nodal_set_error("nodal_dist_pcg: matrix too irregular for the sliced-ELL copy");   // would need an unscaled rebuild
-            return NODAL_BAD_ARG;
+        bool use_sell = (double)sell->padded <= 1.5 * (double)nnz + 1024.0;
+        if (R > 1) {
+            // every rank must take the same path (the scaled operator exists only as SELL): agree
+            int* agree = reinterpret_cast<int*>(sc + (size_t)nloc + nhalo + 2) + 4;
+            const int mine = use_sell ? 1 : 0;
+            CUDA_TRY(cudaMemcpyAsync(agree, &mine, sizeof(int), cudaMemcpyHostToDevice, st));
+            NCCL_TRY(g_nccl.AllReduce(agree, agree, 1, ncclInt32, ncclMin, d->comm, st));
+            int* agree_h = reinterpret_cast<int*>(ctx->pinned) + 8;
+            CUDA_TRY(cudaMemcpyAsync(agree_h, agree, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            use_sell = *agree_h != 0;
         }
+        if (use_sell) A.sell = sell;
+        else unit = false;      // too irregular for SELL-32 (padding > 1.5x): CSR kernels on the unscaled operator
         const int g2_per_sm = getenv("NODAL_DIST_G2") ? atoi(getenv("NODAL_DIST_G2")) : 8;
         const int g2 = (int)std::min<int64_t>((int64_t)ctx->num_sms * g2_per_sm,
                                               std::max<int64_t>(1, ((nloc >> 1) + PCG_THREADS - 1) / PCG_THREADS));

@@ -685,7 +685,7 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
             amg_compose_kernel<<<amg_rows_grid(ctx, nloc), AT, 0, st>>>(nloc, comp, agg);
             KERNEL_CHECK();
         }
-        if (pass + 1 < S.passes && !S.sorted_galerkin) {
+        if (pass + 1 < S.passes && !S.sorted_galerkin && amg_merge_pays(cur.nnz, nc)) {
             // operator the next pass aggregates: the local-local block of P^T A P (couplings to
             // other ranks are invisible to the matching, see amg_core.cuh), merged per coarse row
             int32_t *pp = nullptr, *pi = nullptr;
@@ -738,7 +738,7 @@ int coarsen(Solver& S, DLevel& L, AmgCsr* next, std::vector<int32_t>* next_bound
     KERNEL_CHECK();
     NODAL_TRY(exchange_nccl(S, L.halo, lab, st));
     bool have_members = false;
-    if (!S.sorted_galerkin) {
+    if (!S.sorted_galerkin && amg_merge_pays(nnz, ncur)) {
         // members of the composed aggregates (also the restriction pattern), then one thread merges
         // the member rows of its coarse row with the global coarse column ids
         AmgScratch<int32_t> lab32(ctx, (size_t)L.halo.ext_len + 2);

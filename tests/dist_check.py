@@ -71,6 +71,31 @@ def main():
             runner.pcg.close()
             if rank == 0:
                 print(json.dumps(msg), flush=True)
+    # ---- irregular halos: sparse random networks (first-appearance numbering), expander-like and banded
+    for locality in (None, 200):
+        tn = gen.random_network(20000, degree=8, seed=2, locality=locality)
+        table = copy.deepcopy(tn)
+        table.process_component(["a1", "A", "1", "1", "g"])
+        table = table.table()
+        row = tn.nodenum["1"]
+        r_single = None
+        if rank == 0:
+            csr, rhs = dev.assemble_csr(table)
+            x1, _ = dev.pcg(csr, rhs, rtol=1e-10)
+            r_single = float(x1[row])
+        dtab = dev.upload_table(table)
+        for precond, amg in (("jacobi", {}), ("amg", {"gather_below": 2000})):
+            runner = ndist.GridRunner(dev, table, row, rank, world, rtol=1e-10, precond=precond, amg=amg)
+            r, info = runner.step(dtab)
+            runner.pcg.close()
+            good = info["status"] == 0 and info["relres"] <= 1e-10
+            if rank == 0:
+                good &= abs(r - r_single) <= 1e-9 * abs(r_single)
+                print(json.dumps(dict(random_network=20000, locality=locality, precond=precond, R=r, single_gpu_R=r_single,
+                                      iterations=info["iterations"], halo_recv=info["halo_recv"], status=info["status"],
+                                      ok=bool(good))), flush=True)
+            ok &= good
+
     # ---- the nodal surface under torchrun: Circuit(..., distributed=True) and equivalent_resistance
     import nodal_b200 as n
     import nodal_b200.equiv

@@ -423,6 +423,7 @@ extern "C" int nodal_amg_destroy(nodal_amg* h) {
 extern "C" int nodal_amg_create(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* indptr,
                                 const int32_t* indices, const double* data, const double* params,
                                 nodal_amg** out, void* stream) {
+    NvtxRange nvtx_range("nodal_amg_create");
     if (!ctx || n < 0 || nnz < 0 || !out) return NODAL_BAD_ARG;
     *out = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
@@ -507,6 +508,7 @@ extern "C" int nodal_amg_apply(nodal_ctx* ctx, const nodal_amg* h, const double*
 extern "C" int nodal_amg_pcg(nodal_ctx* ctx, nodal_amg* h, const double* rhs, double* x, double rtol,
                              int32_t maxit, int32_t* iters_h, double* relres_h, double* stats_h,
                              void* stream) {
+    NvtxRange nvtx_range("nodal_amg_pcg");
     if (!ctx || !h || h->ctx != ctx || !iters_h || !relres_h) return NODAL_BAD_ARG;
     *iters_h = 0;
     *relres_h = 0.0;

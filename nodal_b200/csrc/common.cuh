@@ -9,6 +9,17 @@
 
 #include "../../include/nodal_b200.h"
 
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range over a scope (header-only NVTX v3: a no-op unless a profiler is attached), so nsys /
+// ncu timelines show the stages of the path by name.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 typedef unsigned long long u64;
 typedef unsigned int u32;
 

@@ -132,6 +132,7 @@ static thread_local PendingCsr g_pending;
 extern "C" int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
                                uint64_t* keys_, double* vals, double* rhs, int64_t* nnz_h,
                                void* stream) {
+    NvtxRange nvtx_range("nodal_csr_build");
     if (!ctx || n < 0 || nslots < 0 || !nnz_h) return NODAL_BAD_ARG;
     if (nslots >= ((int64_t)1 << 31)) {
         nodal_set_error("nodal_csr_build: more than 2^31 triples are not supported");

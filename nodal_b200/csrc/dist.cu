@@ -824,6 +824,7 @@ extern "C" int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, c
                               const double* data, const double* rhs_local, double* x_local,
                               double rtol, int32_t maxit, int32_t* iters_h, double* relres_h,
                               double* stats_h, void* stream) {
+    NvtxRange nvtx_range("nodal_dist_pcg");
     if (!ctx || !d || !bounds_h || !iters_h || !relres_h) return NODAL_BAD_ARG;
     if (!d->comm) {
         nodal_set_error("nodal_dist_pcg needs a communicator (nodal_dist_create); use nodal_pcg on one GPU");

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <memory>
 #include <vector>
 
 #include "amg_host.cuh"
@@ -903,6 +904,7 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
                                   const double* data, const double* rhs_local, double* x_local,
                                   const double* params, double rtol, int32_t maxit, int32_t* iters_h,
                                   double* relres_h, double* stats_h, void* stream) {
+    NvtxRange nvtx_range("nodal_dist_amg_pcg");
     if (!ctx || !d || !bounds_h || !iters_h || !relres_h) return NODAL_BAD_ARG;
     *iters_h = 0;
     *relres_h = 0.0;
@@ -951,6 +953,7 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
 
     auto run = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ev0, st));
+        std::unique_ptr<NvtxRange> phase(new NvtxRange("amg setup (hierarchy, halo plans, buffers)"));
         // ---------------- level 0 and the distributed coarsening ----------------
         {
             DLevel L;
@@ -1104,7 +1107,10 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
             NODAL_TRY(allreduce(1, part_g, gs, part_d, gs, part_rr, gv, nullptr, 0, nxt, 1, sx));
             return NODAL_OK;
         };
-        NODAL_TRY(start(1));
+        nvtxRangePushA("amg first residual + cycle");
+        const int start_rc = start(1);
+        nvtxRangePop();
+        NODAL_TRY(start_rc);
         const bool use_graph = getenv("NODAL_DIST_NO_GRAPH") == nullptr;
         if (use_graph) {
             const unsigned long long before = g_nodal_launches;
@@ -1121,6 +1127,8 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
             g_nodal_launches = before;
         }
         CUDA_TRY(cudaEventRecord(ev1, st));
+        phase.reset();
+        phase.reset(new NvtxRange("amg-pcg iterations"));
         PcgDev* poll = reinterpret_cast<PcgDev*>(ctx->pinned);
         double last_true_rr = -1.0;
         int par = 0;

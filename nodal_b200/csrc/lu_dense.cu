@@ -435,6 +435,7 @@ lu_gemv_sub_kernel(const double* __restrict__ A, int n, int rb, int re, int cb, 
 
 extern "C" int nodal_lu_solve(nodal_ctx* ctx, int32_t n, double* G, const double* rhs, double* x,
                               int32_t* info_h, void* stream) {
+    NvtxRange nvtx_range("nodal_lu_solve");
     if (!ctx || n < 0 || !info_h) return NODAL_BAD_ARG;
     *info_h = 0;
     if (n == 0) return NODAL_OK;

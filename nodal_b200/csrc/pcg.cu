@@ -25,6 +25,7 @@ extern "C" int nodal_pcg(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t* 
                          const int32_t* indices, const double* data, const double* rhs, double* x,
                          double rtol, int32_t maxit, int32_t flags, int32_t* iters_h,
                          double* relres_h, double* stats_h, void* stream) {
+    NvtxRange nvtx_range("nodal_pcg");
     if (!ctx || n < 0 || !iters_h || !relres_h) return NODAL_BAD_ARG;
     *iters_h = 0;
     *relres_h = 0.0;

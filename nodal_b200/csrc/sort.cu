@@ -453,6 +453,7 @@ size_t radix_sort_scratch_bytes(int64_t count) {
 // *result_in_alt tells where the sorted data ended up.
 int radix_sort_pairs(nodal_ctx* ctx, u64* keys, u64* vals, u64* keys_alt, u64* vals_alt,
                      int64_t count, int bits, bool* result_in_alt, cudaStream_t st) {
+    NvtxRange nvtx_range("radix_sort_pairs");
     *result_in_alt = false;
     if (count <= 1 || bits <= 0) return NODAL_OK;
     int64_t tiles = (count + RS_TILE - 1) / RS_TILE;

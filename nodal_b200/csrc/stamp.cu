@@ -60,6 +60,7 @@ extern "C" int nodal_stamp_coo(nodal_ctx* ctx, int64_t ncomp, const uint8_t* typ
                                const int32_t* c, const int32_t* d, const int32_t* drv,
                                const int32_t* branch, int32_t kcl, int32_t n, int32_t stride,
                                int32_t colbits, uint64_t* keys, double* vals, void* stream) {
+    NvtxRange nvtx_range("nodal_stamp_coo");
     if (!ctx || ncomp < 0 || n < 0 || kcl > n) return NODAL_BAD_ARG;
     if (colbits < 1 || colbits > 31 || ((int64_t)n >> colbits) != 0) {
         nodal_set_error("nodal_stamp_coo: colbits=%d cannot hold column index n=%d", colbits, n);

@@ -9,8 +9,10 @@
 //   h_{j+1,j} = ||w|| ; v_{j+1} = w / h_{j+1,j}
 // Dot products are two-phase and deterministic: per-block partials, then every block of the
 // consumer kernel re-reduces them in a fixed order.  The (m+1) x m Hessenberg least-squares
-// problem is tiny and is updated with Givens rotations on the host (one D2H of <= 2m+1
-// doubles per inner step).
+// problem is tiny and stays on the device: a one-thread kernel applies the Givens rotations after
+// every inner step and freezes the state once the residual estimate meets the tolerance, the
+// host only polls a control word a few steps behind (round 1: a D2H copy and a stream
+// synchronisation per inner step).
 #include <math.h>
 
 #include <algorithm>
@@ -120,6 +122,66 @@ gm_multiaxpy_kernel(int32_t n, const double* __restrict__ V, int nv, double* __r
     }
 }
 
+// Hessenberg state of one restart cycle, kept on the device.
+struct GmCtl {
+    int jdone;       // inner steps whose column has been rotated into H
+    int stop;        // 0 running, 1 converged / lucky breakdown, 2 breakdown (NaN or zero column)
+    double resid;    // |g[jdone]|: residual norm estimate
+};
+
+__global__ void gm_cycle_init_kernel(GmCtl* ctl, double* __restrict__ g, int m, const double* __restrict__ sums) {
+    if (threadIdx.x != 0) return;
+    ctl->jdone = 0;
+    ctl->stop = 0;
+    const double beta = sqrt(sums[0]);
+    ctl->resid = beta;
+    for (int i = 0; i <= m; ++i) g[i] = 0.0;
+    g[0] = beta;
+}
+
+// Column j of H from the step's dot products (hcol[0..j], squared norm of the new vector at
+// hcol[GM_MAXM + 2]): previous rotations, new rotation, g update -- what LAPACK-style GMRES does
+// on the host, one thread.
+__global__ void gm_givens_kernel(int j, int m, const double* __restrict__ hcol_in, double* __restrict__ H,
+                                 double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g,
+                                 GmCtl* ctl, double tol_abs, double tiny) {
+    if (threadIdx.x != 0 || ctl->stop) return;
+    double* hcol = H + (size_t)j * (m + 1);
+    for (int i = 0; i <= j; ++i) hcol[i] = hcol_in[i];
+    const double hn = sqrt(hcol_in[GM_MAXM + 2]);
+    hcol[j + 1] = hn;
+    for (int i = 0; i < j; ++i) {
+        const double a = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
+        hcol[i + 1] = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
+        hcol[i] = a;
+    }
+    const double denom = hypot(hcol[j], hcol[j + 1]);
+    if (denom == 0.0 || !(denom == denom)) { ctl->stop = 2; return; }
+    cs[j] = hcol[j] / denom;
+    sn[j] = hcol[j + 1] / denom;
+    hcol[j] = denom;
+    hcol[j + 1] = 0.0;
+    g[j + 1] = -sn[j] * g[j];
+    g[j] = cs[j] * g[j];
+    ctl->resid = fabs(g[j + 1]);
+    ctl->jdone = j + 1;
+    if (ctl->resid <= tol_abs || hn <= tiny) ctl->stop = 1;
+}
+
+// y = H(0:j,0:j)^-1 g(0:j) for j = jdone, zeros beyond (so x += D^-1 V y can run over every vector
+// the host launched)
+__global__ void gm_solve_y_kernel(int m, int launched, const double* __restrict__ H, const double* __restrict__ g,
+                                  const GmCtl* __restrict__ ctl, double* __restrict__ y) {
+    if (threadIdx.x != 0) return;
+    const int j = ctl->jdone;
+    for (int i = j - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int k = i + 1; k < j; ++k) s -= H[(size_t)k * (m + 1) + i] * y[k];
+        y[i] = s / H[(size_t)i * (m + 1) + i];
+    }
+    for (int i = j; i < launched; ++i) y[i] = 0.0;
+}
+
 // x += D^-1 (V y)
 __global__ void __launch_bounds__(GM_T)
 gm_update_x_kernel(int32_t n, const double* __restrict__ V, int nv, const double* __restrict__ y,
@@ -166,87 +228,98 @@ extern "C" int nodal_gmres(nodal_ctx* ctx, int32_t n, int64_t nnz, const int32_t
     gm_diag_kernel<<<np, GM_T, 0, st>>>(n, indptr, indices, data, dinv);
     KERNEL_CHECK();
 
-    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), y(m, 0.0);
+    // Hessenberg state on the device (pool: the arena above is full of vectors)
+    double* Hd = static_cast<double*>(ctx_pool_alloc(ctx, sizeof(double) * ((size_t)(m + 1) * m + 3 * (size_t)(m + 2)) + 256));
+    if (!Hd) return NODAL_CUDA_ERROR;
+    double* csd = Hd + (size_t)(m + 1) * m;
+    double* snd = csd + (m + 2);
+    double* gd = snd + (m + 2);
+    GmCtl* ctl = reinterpret_cast<GmCtl*>(gd + (m + 2));
+    GmCtl* ctl_h = reinterpret_cast<GmCtl*>(static_cast<char*>(ctx->pinned) + 1024);   // two polling slots
+    cudaEvent_t ev_poll[2];
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_poll[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_poll[1], cudaEventDisableTiming));
+    constexpr int POLL = 4;      // inner steps between two looks at the control word
+
     double bnorm = -1.0, resid = 0.0;
     int total = 0, status = NODAL_NOT_CONVERGED;
     const int max_cycles = std::max(1, (maxit + m - 1) / m) + 1;
-    for (int cycle = 0; cycle < max_cycles; ++cycle) {
-        // true residual r = b - A x  -> v_0
-        NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, x, t, st));
-        gm_residual_kernel<<<np, GM_T, 0, st>>>(n, rhs, t, w, partial, part2);
-        KERNEL_CHECK();
-        gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, part2, V, sums);
-        KERNEL_CHECK();
-        CUDA_TRY(cudaMemcpyAsync(hhost, sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const double beta = sqrt(hhost[0]);
-        if (bnorm < 0.0) bnorm = sqrt(hhost[1]);
-        resid = beta;
-        if (!(beta == beta)) { status = NODAL_BREAKDOWN; break; }
-        if (bnorm == 0.0) {   // b = 0 -> x = 0
-            CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
-            resid = 0.0;
-            status = NODAL_OK;
-            break;
-        }
-        if (beta <= rtol * bnorm) { status = NODAL_OK; break; }
-        if (total >= maxit) break;
-        std::fill(g.begin(), g.end(), 0.0);
-        g[0] = beta;
-        int j = 0;
-        bool lucky = false;
-        for (; j < m && total < maxit; ++j, ++total) {
-            const double* vj = V + (size_t)j * n;
-            double* vn = V + (size_t)(j + 1) * n;
-            gm_mul_kernel<<<np, GM_T, 0, st>>>(n, vj, dinv, t);
+    auto body = [&]() -> int {
+        for (int cycle = 0; cycle < max_cycles; ++cycle) {
+            // true residual r = b - A x  -> v_0
+            NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, x, t, st));
+            gm_residual_kernel<<<np, GM_T, 0, st>>>(n, rhs, t, w, partial, part2);
             KERNEL_CHECK();
-            NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, t, w, st));
-            for (int pass = 0; pass < 2; ++pass) {
-                gm_multidot_kernel<<<np, GM_T, 0, st>>>(n, V, j + 1, w, partial, np);
-                KERNEL_CHECK();
-                gm_multiaxpy_kernel<<<np, GM_T, 0, st>>>(n, V, j + 1, w, partial, np, hdev, pass);
-                KERNEL_CHECK();
-            }
-            gm_multidot_kernel<<<np, GM_T, 0, st>>>(n, V, 0, w, partial, np);
+            gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, part2, V, sums);
             KERNEL_CHECK();
-            gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, nullptr, vn, hdev + GM_MAXM + 2);
-            KERNEL_CHECK();
-            CUDA_TRY(cudaMemcpyAsync(hhost, hdev, sizeof(double) * (GM_MAXM + 4), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(hhost, sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            double* hcol = &H[(size_t)j * (m + 1)];   // column j, rows 0..j+1
-            for (int i = 0; i <= j; ++i) hcol[i] = hhost[i];
-            const double hn = sqrt(hhost[GM_MAXM + 2]);
-            hcol[j + 1] = hn;
-            for (int i = 0; i < j; ++i) {   // previous rotations
-                const double a = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
-                hcol[i + 1] = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
-                hcol[i] = a;
+            const double beta = sqrt(hhost[0]);
+            if (bnorm < 0.0) bnorm = sqrt(hhost[1]);
+            resid = beta;
+            if (!(beta == beta)) { status = NODAL_BREAKDOWN; break; }
+            if (bnorm == 0.0) {   // b = 0 -> x = 0
+                CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
+                resid = 0.0;
+                status = NODAL_OK;
+                break;
             }
-            const double denom = hypot(hcol[j], hcol[j + 1]);
-            if (denom == 0.0 || !(denom == denom)) { status = NODAL_BREAKDOWN; break; }
-            cs[j] = hcol[j] / denom;
-            sn[j] = hcol[j + 1] / denom;
-            hcol[j] = denom;
-            hcol[j + 1] = 0.0;
-            g[j + 1] = -sn[j] * g[j];
-            g[j] = cs[j] * g[j];
-            resid = fabs(g[j + 1]);
-            if (hn <= 1e-300 * bnorm) lucky = true;
-            if (resid <= rtol * bnorm || lucky) { ++j; ++total; break; }
+            if (beta <= rtol * bnorm) { status = NODAL_OK; break; }
+            if (total >= maxit) break;
+            gm_cycle_init_kernel<<<1, 32, 0, st>>>(ctl, gd, m, sums);
+            KERNEL_CHECK();
+            const int budget = std::min(m, maxit - total);
+            int launched = 0, polls = 0;
+            bool stopped = false;
+            for (int j = 0; j < budget && !stopped; ++j) {
+                const double* vj = V + (size_t)j * n;
+                double* vn = V + (size_t)(j + 1) * n;
+                gm_mul_kernel<<<np, GM_T, 0, st>>>(n, vj, dinv, t);
+                KERNEL_CHECK();
+                NODAL_TRY(csr_spmv_launch(ctx, n, nnz, indptr, indices, data, t, w, st));
+                for (int pass = 0; pass < 2; ++pass) {
+                    gm_multidot_kernel<<<np, GM_T, 0, st>>>(n, V, j + 1, w, partial, np);
+                    KERNEL_CHECK();
+                    gm_multiaxpy_kernel<<<np, GM_T, 0, st>>>(n, V, j + 1, w, partial, np, hdev, pass);
+                    KERNEL_CHECK();
+                }
+                gm_multidot_kernel<<<np, GM_T, 0, st>>>(n, V, 0, w, partial, np);
+                KERNEL_CHECK();
+                gm_normalize_kernel<<<np, GM_T, 0, st>>>(n, w, partial, np, nullptr, vn, hdev + GM_MAXM + 2);
+                KERNEL_CHECK();
+                gm_givens_kernel<<<1, 32, 0, st>>>(j, m, hdev, Hd, csd, snd, gd, ctl, rtol * bnorm, 1e-300 * bnorm);
+                KERNEL_CHECK();
+                launched = j + 1;
+                if (launched % POLL == 0) {
+                    // look at the control word one poll behind: the stream never drains
+                    CUDA_TRY(cudaMemcpyAsync(&ctl_h[polls & 1], ctl, sizeof(GmCtl), cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaEventRecord(ev_poll[polls & 1], st));
+                    if (polls >= 1) {
+                        CUDA_TRY(cudaEventSynchronize(ev_poll[(polls - 1) & 1]));
+                        if (ctl_h[(polls - 1) & 1].stop) stopped = true;
+                    }
+                    ++polls;
+                }
+            }
+            // y = H^-1 g over the steps that counted ; x += D^-1 V y
+            gm_solve_y_kernel<<<1, 32, 0, st>>>(m, launched, Hd, gd, ctl, ydev);
+            KERNEL_CHECK();
+            gm_update_x_kernel<<<np, GM_T, 0, st>>>(n, V, launched, ydev, dinv, x);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(&ctl_h[0], ctl, sizeof(GmCtl), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            total += ctl_h[0].jdone;
+            resid = ctl_h[0].resid;
+            if (ctl_h[0].stop == 2) { status = NODAL_BREAKDOWN; break; }
+            if (ctl_h[0].jdone == 0) { status = NODAL_BREAKDOWN; break; }
         }
-        if (status == NODAL_BREAKDOWN) break;
-        // y = H(0:j,0:j)^-1 g(0:j) ; x += D^-1 V y
-        for (int i = j - 1; i >= 0; --i) {
-            double s = g[i];
-            for (int k = i + 1; k < j; ++k) s -= H[(size_t)k * (m + 1) + i] * y[k];
-            y[i] = s / H[(size_t)i * (m + 1) + i];
-        }
-        for (int i = 0; i < j; ++i) hhost[i] = y[i];
-        CUDA_TRY(cudaMemcpyAsync(ydev, hhost, sizeof(double) * (size_t)std::max(j, 1), cudaMemcpyHostToDevice, st));
-        gm_update_x_kernel<<<np, GM_T, 0, st>>>(n, V, j, ydev, dinv, x);
-        KERNEL_CHECK();
-        CUDA_TRY(cudaStreamSynchronize(st));
-    }
+        return NODAL_OK;
+    };
+    const int brc = body();
+    cudaEventDestroy(ev_poll[0]);
+    cudaEventDestroy(ev_poll[1]);
+    ctx_pool_free(ctx, Hd);
+    NODAL_TRY(brc);
     *iters_h = total;
     *relres_h = bnorm > 0.0 ? resid / bnorm : 0.0;
     if (status == NODAL_NOT_CONVERGED) {

@@ -247,6 +247,13 @@ int nodal_dist_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_global, const int32_
                    double rtol, int32_t maxit,
                    int32_t* iters_h, double* relres_h, double* stats_h, void* stream);
 
+/* Several right-hand sides against one hierarchy (many-port equivalent resistance, nodal/equiv.py:31-61
+ * generalised): K <= 8 PCG recurrences advanced together, every level operator read once per sweep for all
+ * of them.  rhs / x: K vectors of n doubles, one after the other (x: initial guesses in, solutions out);
+ * iters_h, relres_h (true residuals), status_h: K entries.  Returns the worst per-system status. */
+int nodal_amg_pcg_multi(nodal_ctx* ctx, nodal_amg* amg, int32_t K, const double* rhs, double* x, double rtol,
+                        int32_t maxit, int32_t* iters_h, double* relres_h, int32_t* status_h, void* stream);
+
 /* Measurement aid for bench.py's roofline entry: average per-launch time (ms, CUDA events on
  * `stream`, `reps` launches after two warm-up launches) of the level-0 SELL sweeps of the hierarchy:
  * ms_out[0] q = A p with the p.q partial sums, [1] r = b - A x, [2] the damped-Jacobi sweep. */

@@ -43,6 +43,35 @@ struct AmgScratch {
     operator T*() const { return ptr; }
 };
 
+// ------------------------------------------------------------------ the hierarchy (amg.cu builds it, amg_multi.cu reads it)
+struct AmgLevel {
+    int32_t n = 0;
+    int64_t nnz = 0;
+    const int32_t* indptr = nullptr;    // CSR of the level operator (level 0: the caller's arrays)
+    const int32_t* indices = nullptr;
+    const double* data = nullptr;
+    bool owned = false;
+    nodal_sell* sell = nullptr;
+    int32_t nc = 0;                     // rows of the next level (0 on the coarsest)
+    int32_t* agg = nullptr;             // [n]  row -> aggregate
+    int32_t* pt_ptr = nullptr;          // [>= nc + 1]  members of every aggregate ...
+    int32_t* pt_idx = nullptr;          // [n]          ... in increasing row order
+    double *b = nullptr, *x = nullptr, *r = nullptr;   // cycle work vectors (b: levels > 0)
+};
+
+struct nodal_amg {
+    nodal_ctx* ctx = nullptr;
+    int device = 0;
+    int passes = 2, coarse = 512, maxlevels = 30, rounds = 8, direct_max = 2048;
+    double omega = 0.8, scale = 1.8, max_fill = 1.2, max_complexity = 4.0;
+    std::vector<AmgLevel> lv;           // lv.back() is the coarsest level
+    double* inv = nullptr;              // [nL x nL] inverse of the coarsest operator (or nullptr)
+    double *p = nullptr, *q = nullptr, *r = nullptr, *z = nullptr;   // CG vectors
+    double* part = nullptr;             // 3 x nparts partial sums + scalars
+    int nparts = 0;
+    float setup_ms = 0.f;
+};
+
 struct AmgCsr {
     int32_t n = 0;
     int64_t nnz = 0;

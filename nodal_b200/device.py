@@ -126,6 +126,23 @@ class DeviceAMG:
                    "nodal_amg_apply")
         return z
 
+    def solve_multi(self, rhs, rtol=1e-10, maxit=None):
+        """Several right-hand sides at once: rhs is a (K, n) device tensor, K <= 8; returns x (K, n) and
+        a list of K info dicts (csrc/amg_multi.cu: every level operator is read once per sweep for all K)."""
+        dev, n = self.dev, self.csr.n
+        K = int(rhs.shape[0])
+        if not 1 <= K <= 8 or int(rhs.shape[1]) != n:
+            raise ValueError("rhs must be a (K, n) tensor with 1 <= K <= 8")
+        rhs = rhs.contiguous()
+        x = dev.zeros(max(2, K * n), dev.torch.float64)[: K * n].view(K, n)
+        iters, relres, status = (C.c_int32 * K)(), (C.c_double * K)(), (C.c_int32 * K)()
+        st = dev.lib.nodal_amg_pcg_multi(dev.ctx, self.handle, K, dev.ptr(rhs), dev.ptr(x), rtol, int(maxit or 1000),
+                                         iters, relres, status, dev.stream())
+        _lib.check(st, "nodal_amg_pcg_multi", allowed=(_lib.OK, _lib.NOT_CONVERGED, _lib.BREAKDOWN))
+        infos = [dict(solver="amg_pcg_multi", status=int(status[k]), iterations=int(iters[k]), relres=float(relres[k]),
+                      batch=K, level_rows=list(self.rows)) for k in range(K)]
+        return x, infos
+
     def profile_sweeps(self, reps=64):
         """Average ms per launch of the level-0 SELL sweeps: dict(spmv_dot, residual, jacobi)."""
         ms = (C.c_double * 4)()

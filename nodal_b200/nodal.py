@@ -530,6 +530,39 @@ class Circuit:
                 amg = None             # _device_solve retries per right-hand side and falls back to Jacobi
         values, stats = [], []
         try:
+            if amg is not None and self.options.get("multi_rhs", True):
+                # several ports against one hierarchy: batches of up to 8 right-hand sides advance
+                # together, every level operator is read once per sweep for the whole batch
+                # (csrc/amg_multi.cu); a batch that does not converge is redone pair by pair below
+                rows_of = [(row(a), row(b)) for a, b in pairs]
+                todo = [k for k, (ia, ib) in enumerate(rows_of) if ia != ib]
+                done = {}
+                for start in range(0, len(todo), 8):
+                    batch = todo[start:start + 8]
+                    rhs = dev.zeros(max(2, len(batch) * n), torch.float64)[: len(batch) * n].view(len(batch), n)
+                    for j, k in enumerate(batch):
+                        ia, ib = rows_of[k]
+                        if ia != c.GROUND:
+                            rhs[j, ia] = 1.0
+                        if ib != c.GROUND:
+                            rhs[j, ib] = -1.0
+                    xs, infos = amg.solve_multi(rhs, rtol=self.options.get("rtol", 1e-10), maxit=self.options.get("maxit"))
+                    for j, k in enumerate(batch):
+                        if infos[j]["status"] == 0:
+                            ia, ib = rows_of[k]
+                            ea = float(xs[j, ia]) if ia != c.GROUND else 0.0
+                            eb = float(xs[j, ib]) if ib != c.GROUND else 0.0
+                            done[k] = (ea - eb, infos[j])
+                if len(done) == len(todo):
+                    for k, (ia, ib) in enumerate(rows_of):
+                        if ia == ib:
+                            values.append(0.0)
+                            stats.append(dict(solver="none", status=0, iterations=0))
+                        else:
+                            values.append(done[k][0])
+                            stats.append(done[k][1])
+                    self.stats = stats
+                    return values
             for a, b in pairs:
                 ia, ib = row(a), row(b)
                 if ia == ib:

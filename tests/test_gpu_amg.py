@@ -166,8 +166,8 @@ def test_many_port_equivalent_resistances(device, mode):
         want = orc.equivalent_resistance(rows, a, b, sparse=True)
         assert r == pytest.approx(want, rel=1e-9)
         assert r == pytest.approx(n.equiv.equivalent_resistance(net, a, b, **kw), rel=1e-9)
-        if mode == "amg":
-            assert st["solver"] == "amg_pcg" and st["levels"] >= 2
+        if mode == "amg":       # several pairs: the batched solver (all right-hand sides advance together)
+            assert st["solver"] == "amg_pcg_multi" and len(st["level_rows"]) >= 2 and st["relres"] <= 1e-12
     assert got[0] == pytest.approx(got[1], rel=1e-12)    # symmetric in (a, b)
     with pytest.raises(KeyError):
         n.equiv.equivalent_resistances(net, [("1", "nowhere")], **kw)
@@ -206,3 +206,45 @@ def test_dist_amg_single_rank(device, N, amg):
     resid = device.spmv(csr, x) - rhs
     assert float(resid.norm() / rhs.norm()) <= 1.05e-10
     assert float((x - x1).abs().max()) <= 1e-8 * float(x1.abs().max())
+
+
+def test_multi_rhs_solver_matches_single_solves(device):
+    """csrc/amg_multi.cu: K right-hand sides against one hierarchy, each equal to its own single
+    solve (to the tolerance) with a similar iteration count; zero and duplicate right-hand sides,
+    more than one batch, and the single-pair path of port_resistances stay consistent."""
+    import torch
+    net = gen.grid2d(120)
+    table = net.table()
+    csr, _ = device.assemble_csr(table)
+    amg = device.amg(csr)
+    try:
+        rng = np.random.default_rng(5)
+        K = 8
+        rhs = torch.zeros(K, csr.n, dtype=torch.float64, device="cuda")
+        picks = rng.choice(csr.n, size=(K, 2), replace=False)
+        for k in range(K):
+            rhs[k, picks[k, 0]] = 1.0
+            rhs[k, picks[k, 1]] = -1.0
+        rhs[3] = 0.0                                   # b = 0 -> x = 0, no iterations
+        rhs[5] = rhs[1]                                # duplicates converge together
+        xs, infos = amg.solve_multi(rhs, rtol=1e-11)
+        for k in range(K):
+            assert infos[k]["status"] == 0 and infos[k]["relres"] <= 1e-11, infos[k]
+            if k == 3:
+                assert infos[k]["iterations"] == 0 and float(xs[k].abs().max()) == 0.0
+                continue
+            x1, i1 = amg.solve(rhs[k].clone(), rtol=1e-11)
+            assert abs(infos[k]["iterations"] - i1["iterations"]) <= 3
+            assert float((xs[k] - x1).abs().max()) <= 1e-8 * float(x1.abs().max())
+            resid = device.spmv(csr, xs[k].contiguous()) - rhs[k]
+            assert float(resid.norm() / rhs[k].norm()) <= 1.05e-11
+        assert torch.equal(xs[5], xs[1])
+    finally:
+        amg.close()
+    # 11 pairs = two batches; equal to pair-by-pair solves
+    pairs = [("1", "g")] + [(f"n{3 * k}_{2 * k}", f"n{100 - k}_{90 - 2 * k}") for k in range(10)]
+    batched = n.equiv.equivalent_resistances(net, pairs, sparse=True, precond="amg")
+    single = n.equiv.equivalent_resistances(net, pairs, sparse=True, precond="amg", multi_rhs=False)
+    assert all(st["solver"] == "amg_pcg_multi" for st in n.equiv.equivalent_resistances.last_stats) is False
+    for rb, rs in zip(batched, single):
+        assert rb == pytest.approx(rs, rel=1e-8)

@@ -244,7 +244,8 @@ def test_multi_rhs_solver_matches_single_solves(device):
     # 11 pairs = two batches; equal to pair-by-pair solves
     pairs = [("1", "g")] + [(f"n{3 * k}_{2 * k}", f"n{100 - k}_{90 - 2 * k}") for k in range(10)]
     batched = n.equiv.equivalent_resistances(net, pairs, sparse=True, precond="amg")
+    assert all(st["solver"] == "amg_pcg_multi" for st in n.equiv.equivalent_resistances.last_stats)
     single = n.equiv.equivalent_resistances(net, pairs, sparse=True, precond="amg", multi_rhs=False)
-    assert all(st["solver"] == "amg_pcg_multi" for st in n.equiv.equivalent_resistances.last_stats) is False
+    assert all(st["solver"] == "amg_pcg" for st in n.equiv.equivalent_resistances.last_stats)
     for rb, rs in zip(batched, single):
         assert rb == pytest.approx(rs, rel=1e-8)

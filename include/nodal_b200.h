@@ -96,6 +96,14 @@ int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
                     int64_t* nnz_h, void* stream);
 int nodal_csr_fetch(nodal_ctx* ctx, int32_t n, int64_t nnz,
                     int32_t* indptr, int32_t* indices, double* data, void* stream);
+/* nodal_csr_build with the column order chosen: order 0 = sorted (what nodal_csr_build gives and what
+ * scipy's spsolve leaves in circuit.G), order 1 = first touch, the order `G.tocsr()` of the reference's DOK
+ * matrix has before the solve (nodal/nodal.py:396-397): within a row, columns appear in the order their
+ * keys were inserted; a key whose running sum hit exact zero was deleted and counts from its re-insertion.
+ * Followed by nodal_csr_fetch as usual.  Values are identical in both orders. */
+int nodal_csr_build_ordered(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
+                            uint64_t* keys, double* vals, int32_t order, double* rhs, int64_t* nnz_h,
+                            void* stream);
 
 /* CSR -> dense row-major n x n (dense mode of build_model, nodal/nodal.py:352-353).
  * G is fully overwritten. */

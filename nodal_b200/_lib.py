@@ -27,6 +27,7 @@ SIGNATURES = {
     "nodal_stamp_coo": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "nodal_csr_build": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "nodal_csr_build_ordered": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, C.POINTER(_i64), _vp]),
     "nodal_csr_fetch": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "nodal_csr_to_dense": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nodal_coo_to_dense_atomic": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),

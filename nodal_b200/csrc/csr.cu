@@ -47,6 +47,77 @@ segment_sum_kernel(const u64* __restrict__ keys, const double* __restrict__ vals
     }
 }
 
+// First-touch variant (the column order scipy's DOK -> CSR conversion leaves, nodal/nodal.py:396-397
+// before spsolve sorts the indices in place): the sort's payload is the emission index, values are
+// gathered through it, and every unique entry remembers the emission at which its key was
+// (re-)inserted -- a DOK key whose running sum hits exact zero is deleted and a later `+=`
+// re-inserts it at the END of the dict order.
+__global__ void __launch_bounds__(CB_THREADS)
+iota_u64_kernel(int64_t count, u64* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (u64)i;
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+segment_sum_first_touch_kernel(const u64* __restrict__ keys, const u64* __restrict__ idx, const double* __restrict__ vals,
+                               int64_t count, int32_t n, int colbits, const u32* __restrict__ head_scan,
+                               u64* __restrict__ ukey, double* __restrict__ uval, u32* __restrict__ keep,
+                               u32* __restrict__ ufirst, double* __restrict__ rhs) {
+    const u64 colmask = ((u64)1 << colbits) - 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const u64 k = keys[i];
+        if ((int64_t)(k >> colbits) >= (int64_t)n) continue;
+        if (i != 0 && keys[i - 1] == k) continue;
+        double s = 0.0;
+        bool absent = true;
+        u32 first = 0;
+        for (int64_t j = i; j < count && keys[j] == k; ++j) {
+            const double t = s + vals[idx[j]];
+            if (t != 0.0) {
+                if (absent) { first = (u32)idx[j]; absent = false; }
+            } else {
+                absent = true;
+            }
+            s = absent ? 0.0 : t;
+        }
+        const u32 seg = head_scan[i];
+        const int32_t col = (int32_t)(k & colmask);
+        ukey[seg] = k;
+        uval[seg] = s;
+        ufirst[seg] = first;
+        if (col == n) {
+            rhs[(int32_t)(k >> colbits)] = s;
+            keep[seg] = 0u;
+        } else {
+            keep[seg] = absent ? 0u : 1u;
+        }
+    }
+}
+
+// kept entries in sorted order -> key (row, first-touch emission) and their position
+__global__ void __launch_bounds__(CB_THREADS)
+first_touch_keys_kernel(const u64* __restrict__ ukey, const u32* __restrict__ ufirst, const u32* __restrict__ keep_scan,
+                        const u32* __restrict__ keep, int64_t useg, int colbits, u64* __restrict__ keys2,
+                        u64* __restrict__ pos2) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < useg; s += (int64_t)gridDim.x * blockDim.x) {
+        if (!keep[s]) continue;
+        const u32 p = keep_scan[s];
+        keys2[p] = ((ukey[s] >> colbits) << 32) | (u64)ufirst[s];
+        pos2[p] = (u64)p;
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+permute_entries_kernel(int64_t nnz, const u64* __restrict__ pos, const int32_t* __restrict__ cols_in,
+                       const double* __restrict__ vals_in, int32_t* __restrict__ cols_out, double* __restrict__ vals_out) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        const u64 p = pos[q];
+        cols_out[q] = cols_in[p];
+        vals_out[q] = vals_in[p];
+    }
+}
+
 __global__ void __launch_bounds__(CB_THREADS)
 compact_kernel(const u64* __restrict__ ukey, const double* __restrict__ uval,
                const u32* __restrict__ keep_scan, const u32* __restrict__ keep_flag_src,
@@ -122,6 +193,8 @@ struct PendingCsr {
     const u32* keep = nullptr;
     const u32* keep_scan = nullptr;
     int32_t* krow = nullptr;
+    const u32* ufirst = nullptr;      // first-touch order only
+    int order = 0;
     int64_t useg = 0, nnz = 0;
     int32_t n = 0;
     int colbits = 0;
@@ -129,9 +202,24 @@ struct PendingCsr {
 };
 static thread_local PendingCsr g_pending;
 
+static int csr_build_impl(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits, uint64_t* keys_, double* vals,
+                          double* rhs, int64_t* nnz_h, void* stream, int order);
+
 extern "C" int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
                                uint64_t* keys_, double* vals, double* rhs, int64_t* nnz_h,
                                void* stream) {
+    return csr_build_impl(ctx, n, nslots, colbits, keys_, vals, rhs, nnz_h, stream, 0);
+}
+
+extern "C" int nodal_csr_build_ordered(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits,
+                                       uint64_t* keys_, double* vals, int32_t order, double* rhs,
+                                       int64_t* nnz_h, void* stream) {
+    if (order != 0 && order != 1) return NODAL_BAD_ARG;
+    return csr_build_impl(ctx, n, nslots, colbits, keys_, vals, rhs, nnz_h, stream, order);
+}
+
+static int csr_build_impl(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_t colbits, uint64_t* keys_, double* vals,
+                          double* rhs, int64_t* nnz_h, void* stream, int order) {
     NvtxRange nvtx_range("nodal_csr_build");
     if (!ctx || n < 0 || nslots < 0 || !nnz_h) return NODAL_BAD_ARG;
     if (nslots >= ((int64_t)1 << 31)) {
@@ -158,9 +246,15 @@ extern "C" int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_
     const size_t slots = (size_t)nslots;
     size_t need = 2 * align_up(slots * 8, 256) + 3 * align_up(slots * 4, 256) +
                   radix_sort_scratch_bytes(nslots) + 2 * scan_scratch_bytes(nslots) + (1 << 16);
+    if (order == 1) need += 2 * align_up(slots * 8, 256) + align_up(slots * 4, 256);
     NODAL_TRY(ctx_reserve(ctx, need));
     u64* keys_alt = carve<u64>(ctx, slots);
     u64* vals_alt = carve<u64>(ctx, slots);
+    // first-touch order: the sort carries emission indices, the values stay where they are
+    u64* idx = order == 1 ? carve<u64>(ctx, slots) : nullptr;
+    double* usum = order == 1 ? carve<double>(ctx, slots) : nullptr;
+    u32* ufirst = order == 1 ? carve<u32>(ctx, slots) : nullptr;
+    if (order == 1 && (!idx || !usum || !ufirst)) return NODAL_CUDA_ERROR;
     u32* head = carve<u32>(ctx, slots);      // head flags -> scan; later reused as krow
     u32* keep = carve<u32>(ctx, slots);      // keep flags per unique key
     u32* keep_scan = carve<u32>(ctx, slots);
@@ -169,21 +263,29 @@ extern "C" int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_
 
     bool in_alt = false;
     const size_t mark = ctx->arena_used;
-    NODAL_TRY(radix_sort_pairs(ctx, keys, reinterpret_cast<u64*>(vals), keys_alt, vals_alt, nslots,
+    const int grid = grid_for(ctx, nslots, CB_THREADS);
+    if (order == 1) {
+        iota_u64_kernel<<<grid, CB_THREADS, 0, st>>>(nslots, idx);
+        KERNEL_CHECK();
+    }
+    NODAL_TRY(radix_sort_pairs(ctx, keys, order == 1 ? idx : reinterpret_cast<u64*>(vals), keys_alt, vals_alt, nslots,
                                bits, &in_alt, st));
     ctx->arena_used = mark;
     const u64* sk = in_alt ? keys_alt : keys;
     const double* sv = in_alt ? reinterpret_cast<double*>(vals_alt) : vals;
+    const u64* sidx = in_alt ? vals_alt : idx;
     u64* ukey = in_alt ? keys : keys_alt;  // the other pair is free now
-    double* uval = in_alt ? vals : reinterpret_cast<double*>(vals_alt);
+    double* uval = order == 1 ? usum : (in_alt ? vals : reinterpret_cast<double*>(vals_alt));
 
-    const int grid = grid_for(ctx, nslots, CB_THREADS);
     mark_heads_kernel<<<grid, CB_THREADS, 0, st>>>(sk, nslots, n, colbits, head);
     KERNEL_CHECK();
     NODAL_TRY(scan_exclusive_u32(ctx, head, head, nslots, totals + 0, st));
     ctx->arena_used = mark;
-    segment_sum_kernel<<<grid, CB_THREADS, 0, st>>>(sk, sv, nslots, n, colbits, head, ukey, uval,
-                                                    keep, rhs);
+    if (order == 1)
+        segment_sum_first_touch_kernel<<<grid, CB_THREADS, 0, st>>>(sk, sidx, vals, nslots, n, colbits, head, ukey, uval,
+                                                                    keep, ufirst, rhs);
+    else
+        segment_sum_kernel<<<grid, CB_THREADS, 0, st>>>(sk, sv, nslots, n, colbits, head, ukey, uval, keep, rhs);
     KERNEL_CHECK();
     u32* host_tot = reinterpret_cast<u32*>(ctx->pinned);
     CUDA_TRY(cudaMemcpyAsync(host_tot, totals, sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -201,6 +303,8 @@ extern "C" int nodal_csr_build(nodal_ctx* ctx, int32_t n, int64_t nslots, int32_
     g_pending.keep = keep;
     g_pending.keep_scan = keep_scan;
     g_pending.krow = reinterpret_cast<int32_t*>(head);
+    g_pending.ufirst = ufirst;
+    g_pending.order = order;
     g_pending.useg = useg;
     g_pending.nnz = nnz;
     g_pending.n = n;
@@ -237,6 +341,43 @@ extern "C" int nodal_csr_fetch(nodal_ctx* ctx, int32_t n, int64_t nnz, int32_t* 
     row_ptr_gaps_kernel<<<ctx->num_sms * 4, CB_THREADS, 0, st>>>(indptr, gaps, ngaps);
     KERNEL_CHECK();
     ctx_pool_free(ctx, gaps);   // stream-ordered reuse only
+    if (p.order == 1 && nnz > 1) {
+        // entries of every row by first-touch emission: stable sort of (row, emission) over the kept
+        // entries, then gather (pool buffers: the arena still holds the pending result)
+        int rowbits = 1;
+        while (((int64_t)n >> rowbits) != 0) ++rowbits;
+        const size_t cnt = (size_t)nnz;
+        u64* k2 = static_cast<u64*>(ctx_pool_alloc(ctx, cnt * 8));
+        u64* p2 = static_cast<u64*>(ctx_pool_alloc(ctx, cnt * 8));
+        u64* k2a = static_cast<u64*>(ctx_pool_alloc(ctx, cnt * 8));
+        u64* p2a = static_cast<u64*>(ctx_pool_alloc(ctx, cnt * 8));
+        int32_t* ctmp = static_cast<int32_t*>(ctx_pool_alloc(ctx, cnt * 4));
+        double* vtmp = static_cast<double*>(ctx_pool_alloc(ctx, cnt * 8));
+        char* sort_ws = static_cast<char*>(ctx_pool_alloc(ctx, radix_sort_scratch_bytes(nnz) + 4096));
+        int rc = (k2 && p2 && k2a && p2a && ctmp && vtmp && sort_ws) ? NODAL_OK : NODAL_CUDA_ERROR;
+        if (rc == NODAL_OK) {
+            first_touch_keys_kernel<<<grid_for(ctx, p.useg, CB_THREADS), CB_THREADS, 0, st>>>(
+                p.ukey, p.ufirst, p.keep_scan, p.keep, p.useg, p.colbits, k2, p2);
+            ++g_nodal_launches;
+            // the sort carves its scratch from the arena: lend it a private one for this call
+            char* arena = ctx->arena; const size_t bytes = ctx->arena_bytes, used = ctx->arena_used;
+            ctx->arena = sort_ws; ctx->arena_bytes = radix_sort_scratch_bytes(nnz) + 4096; ctx->arena_used = 0;
+            bool in_alt = false;
+            rc = radix_sort_pairs(ctx, k2, p2, k2a, p2a, nnz, 32 + rowbits, &in_alt, st);
+            ctx->arena = arena; ctx->arena_bytes = bytes; ctx->arena_used = used;
+            if (rc == NODAL_OK) {
+                cudaMemcpyAsync(ctmp, indices, cnt * 4, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync(vtmp, data, cnt * 8, cudaMemcpyDeviceToDevice, st);
+                permute_entries_kernel<<<grid_for(ctx, nnz, CB_THREADS), CB_THREADS, 0, st>>>(
+                    nnz, in_alt ? p2a : p2, ctmp, vtmp, indices, data);
+                ++g_nodal_launches;
+                if (cudaGetLastError() != cudaSuccess) rc = NODAL_CUDA_ERROR;
+            }
+        }
+        for (void* q : {(void*)k2, (void*)p2, (void*)k2a, (void*)p2a, (void*)ctmp, (void*)vtmp, (void*)sort_ws})
+            ctx_pool_free(ctx, q);
+        if (rc != NODAL_OK) { g_pending = PendingCsr(); return rc; }
+    }
     g_pending = PendingCsr();
     return NODAL_OK;
 }

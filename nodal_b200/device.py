@@ -251,21 +251,26 @@ class Device:
             kcl, n, stride, cb, p(keys), p(vals), self.stream()), "nodal_stamp_coo")
         return keys, vals, cb
 
-    def assemble_csr(self, table: ComponentTable, dtab=None):
-        """Stamp + CSR build.  Returns (DeviceCSR, rhs tensor)."""
+    def assemble_csr(self, table: ComponentTable, dtab=None, order="sorted"):
+        """Stamp + CSR build.  Returns (DeviceCSR, rhs tensor).  order="first_touch" keeps the columns
+        of a row in the order the reference's DOK matrix met them (what `G.tocsr()` gives before
+        spsolve sorts it, nodal/nodal.py:396-397); the solvers expect the default, sorted order."""
         if dtab is None:
             dtab = self.upload_table(table)
-        return self.assemble_csr_raw(dtab, len(table), table.kcl, table.n, coo_stride(table))
+        return self.assemble_csr_raw(dtab, len(table), table.kcl, table.n, coo_stride(table), order=order)
 
-    def assemble_csr_raw(self, dtab, ncomp, kcl, n, stride):
+    def assemble_csr_raw(self, dtab, ncomp, kcl, n, stride, order="sorted"):
         """The same from device-resident columns (`dtab`: name -> tensor, `ncomp` rows used)."""
         torch = self.torch
+        if order not in ("sorted", "first_touch"):
+            raise ValueError("order must be 'sorted' or 'first_touch'")
         keys, vals, cb = self.stamp_coo(dtab, ncomp, kcl, n, stride)
         rhs = self.empty(max(1, n), torch.float64)[:n]
         nnz = C.c_int64(0)
         p = self.ptr
-        _lib.check(self.lib.nodal_csr_build(self.ctx, n, stride * ncomp, cb, p(keys), p(vals),
-                                            p(rhs), C.byref(nnz), self.stream()), "nodal_csr_build")
+        _lib.check(self.lib.nodal_csr_build_ordered(self.ctx, n, stride * ncomp, cb, p(keys), p(vals),
+                                                    1 if order == "first_touch" else 0, p(rhs), C.byref(nnz),
+                                                    self.stream()), "nodal_csr_build")
         nnz = nnz.value
         indptr = self.empty(n + 1, torch.int32)
         indices = self.empty(max(1, nnz), torch.int32)[:nnz]

@@ -279,7 +279,12 @@ class Circuit:
         if self.options.get("distributed"):
             G, A = self._build_distributed(dev, table)
         elif self.sparse:
-            G, A = dev.assemble_csr(table)
+            # csr_order="first_touch": G's columns in the order the reference's G.tocsr() has before its
+            # solve (nodal.py:396-397); the solve then works on the sorted form, as spsolve sorts in place
+            order = self.options.get("csr_order", "sorted")
+            G, A = dev.assemble_csr(table, order=order)
+            if order != "sorted":
+                self._G_sorted = dev.assemble_csr(table)[0]
         else:
             G, A = dev.assemble_dense(table, atomic=bool(self.options.get("atomic_stamp", False)))
         logging.debug(f"currents={currents}")
@@ -335,6 +340,9 @@ class Circuit:
             return dev.lu_solve(self.G.clone(), rhs)
         kind = self._sparse_solver()
         rtol = self.options.get("rtol", 1e-10)
+        if getattr(self, "_G_sorted", None) is not None:
+            self.G = self._G_sorted        # spsolve leaves circuit.G with sorted indices too
+            self._G_sorted = None
         if self._dist is not None:
             if kind == "gmres":
                 raise NotImplementedError("row-partitioned solve is implemented for R / A netlists")

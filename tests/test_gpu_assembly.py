@@ -50,6 +50,16 @@ def test_doc_netlists_bit_exact(device, name, tmp_path):
     assert cs.G.indices.dtype == device.torch.int32
     assert cs.A_host.tolist() == g["A"]
     assert cs.currents == g["currents"]
+    # the column order G.tocsr() has in the reference BEFORE the solve sorts it (first touch, with DOK's
+    # delete-on-zero / re-insert rule), bit for bit; solving then leaves the sorted form, as spsolve does
+    ft = n.Circuit(net, sparse=True, csr_order="first_touch")
+    wf = g["csr_first_touch"]
+    assert ft.G.indptr.cpu().numpy().tolist() == wf["indptr"]
+    assert ft.G.indices.cpu().numpy().tolist() == wf["indices"]
+    assert ft.G.data.cpu().numpy().tolist() == wf["data"]
+    if "result_sparse" in g and all(v is not None for v in g["result_sparse"]):
+        ft.solve()
+        assert ft.G.indices.cpu().numpy().tolist() == want["indices"]
     cd = n.Circuit(net, sparse=False)
     assert np.array_equal(cd.G_host, np.array(g["G"]))
     assert cd.A_host.tolist() == g["A"]
@@ -68,6 +78,12 @@ def test_grids_bit_exact(device, key):
     assert csr.indptr.cpu().numpy().tolist() == want["indptr"]
     assert csr.indices.cpu().numpy().tolist() == want["indices"]
     assert csr.data.cpu().numpy().tolist() == want["data"]
+    if "csr_first_touch" in g:
+        cf, _ = device.assemble_csr(tn.table(), order="first_touch")
+        wf = g["csr_first_touch"]
+        assert cf.indptr.cpu().numpy().tolist() == wf["indptr"]
+        assert cf.indices.cpu().numpy().tolist() == wf["indices"]
+        assert cf.data.cpu().numpy().tolist() == wf["data"]
     assert not rhs.cpu().numpy().any()
 
 

@@ -1145,6 +1145,14 @@ extern "C" int nodal_dist_amg_pcg(nodal_ctx* ctx, nodal_dist* d, int32_t n_globa
                 par ^= 1;
                 CUDA_TRY(cudaMemcpyAsync(&poll[k & 1], dev, sizeof(PcgDev), cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaEventRecord(ev_poll[k & 1], st));
+                if (R > 1 && !use_mail) {
+                    // NCCL back end: the collectives inside an iteration do not look at the `done` word,
+                    // so every rank must launch exactly the same number of iterations: no look-ahead
+                    CUDA_TRY(cudaEventSynchronize(ev_poll[k & 1]));
+                    if (poll[k & 1].done) break;
+                    if (k > max_iters) break;
+                    continue;
+                }
                 if (k >= 1) {
                     CUDA_TRY(cudaEventSynchronize(ev_poll[(k - 1) & 1]));
                     if (poll[(k - 1) & 1].done) break;

@@ -340,6 +340,7 @@ class Circuit:
             return dev.lu_solve(self.G.clone(), rhs)
         kind = self._sparse_solver()
         rtol = self.options.get("rtol", 1e-10)
+        warm = self._warm_start()
         if getattr(self, "_G_sorted", None) is not None:
             self.G = self._G_sorted        # spsolve leaves circuit.G with sorted indices too
             self._G_sorted = None
@@ -359,7 +360,7 @@ class Circuit:
             if first:
                 info["fallback_from_amg"] = first
             return x, info
-        if kind == "amg" and amg is None and self.options.get("precond", "auto") == "auto":
+        if kind == "amg" and amg is None and warm is None and self.options.get("precond", "auto") == "auto":
             # "auto": which preconditioner pays depends on the graph, not on its size -- on a 4 M-node
             # expander-like random network Jacobi-PCG needs 98 iterations (43 ms) and the AMG hierarchy
             # 265 ms; on a banded random network of the same size it is 4 616 iterations (1.9 s)
@@ -388,10 +389,10 @@ class Circuit:
                     info["iterations_probe"] = info0["iterations"]
                 return x, info
         if kind == "amg":
-            return self._amg_solve(rhs, amg, rtol, None)
+            return self._amg_solve(rhs, amg, rtol, warm)
         if kind == "pcg":
             return dev.pcg(self.G, rhs, rtol=rtol, maxit=self.options.get("maxit"),
-                           flags=self.options.get("pcg_flags", 0))
+                           flags=self.options.get("pcg_flags", 0), x0=warm)
         x, info = dev.gmres(self.G, rhs, rtol=self.options.get("rtol", 1e-12),
                             restart=self.options.get("restart", 60),
                             maxit=self.options.get("maxit") or 20000)
@@ -412,6 +413,17 @@ class Circuit:
             info["note"] = (f"gmres did not converge (relres {info['relres']:.2e}) and the system has more than "
                             f"{limit} rows (dense fallback limit)")
         return x, info
+
+    def _warm_start(self):
+        """Initial guess of the iterative solvers: Circuit(..., x0=array of n values) -- e.g. the
+        previous solution of a parameter sweep.  None: start from zero."""
+        x0 = self.options.get("x0")
+        if x0 is None or not self.sparse or self._dist is not None:
+            return None
+        arr = np.ascontiguousarray(x0, dtype=np.float64)
+        if arr.shape != (self.table.n,):
+            raise ValueError(f"x0 must have {self.table.n} entries")
+        return self._dev.to_device(arr)
 
     def _amg_solve(self, rhs, amg, rtol, x0):
         """AMG-preconditioned CG on one GPU; Jacobi-PCG retry unless precond="amg" was forced."""

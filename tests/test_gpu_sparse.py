@@ -256,3 +256,17 @@ def test_random_network_equivalent_resistance(device, locality):
     # the probe sends the expander-like graph (71 CG iterations on the CPU) to Jacobi; the banded one
     # (293) is near the threshold at this size and may go either way
     assert picked.startswith("jacobi") if locality is None else picked != "", picked
+
+
+def test_circuit_warm_start(device):
+    """Circuit(..., x0=previous solution): the iterative solvers start from it."""
+    import copy
+    net = copy.deepcopy(gen.grid2d(200))
+    net.process_component(["a1", "A", "1", "1", "g"])
+    for precond in ("jacobi", "amg"):
+        cold = n.Circuit(net, sparse=True, precond=precond).solve()
+        warm = n.Circuit(net, sparse=True, precond=precond, x0=cold.result).solve()
+        assert warm.stats["status"] == 0 and warm.stats["iterations"] <= 2 < cold.stats["iterations"]
+        assert np.allclose(warm.result, cold.result, rtol=0, atol=1e-9 * np.abs(cold.result).max())
+    with pytest.raises(ValueError):
+        n.Circuit(net, sparse=True, x0=np.zeros(3)).solve()

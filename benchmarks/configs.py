@@ -63,8 +63,22 @@ def main():
     ap.add_argument("--c4-batch", type=int, default=1_000_000)
     ap.add_argument("--c5b", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-c4", action="store_true", help="batched LU only (both value layouts)")
     args = ap.parse_args()
     dev = Device.get(0)
+    if args.only_c4:
+        net = n.Netlist(write_csv(gen.OPAMP_AMPLIFIER_ROWS))
+        table = net.table()
+        vals = gen.opamp_sweep_values(args.c4_batch, seed=0)
+        d_aos = dev.to_device(vals)
+        d_soa = dev.to_device(np.ascontiguousarray(vals.T))
+        ms_a, (xa, ia) = timed(lambda: dev.lu_batched(table, d_aos), warmup=2, reps=10)
+        ms_s, (xs, i_s) = timed(lambda: dev.lu_batched(table, d_soa, layout="soa"), warmup=2, reps=10)
+        same = bool(torch.equal(xa, xs.t().contiguous()))
+        emit(config="C4", batch=args.c4_batch, aos_ms=ms_a, soa_ms=ms_s, aos_gbs=96.0 * args.c4_batch / ms_a / 1e6,
+             soa_gbs=96.0 * args.c4_batch / ms_s / 1e6, soa_equals_aos_bitwise=same,
+             singular=int((ia != 0).sum().item()) + int((i_s != 0).sum().item()))
+        return
 
     # ---- C1: latency of the smallest dense case
     rows = [["r1", "R", "2", "1", "4"], ["r2", "R", "2", "1", "g"], ["r3", "R", "0.5", "1", "2"],

@@ -26,6 +26,10 @@ GOLD = {20: 0.7806032927398155, 50: 0.7743468244758764, 100: 0.7735139127312641,
         400: 0.7732566450916762, 1000: 0.7732422803670024}
 
 
+# level sizes of amg_mirror.AMG(grid_matrix(N)[0], partitions=2, gather_below=g) (computed on the CPU)
+MIRROR_ROWS_2_RANKS = {(100, 300): [9999, 2057, 425], (400, 4000): [159999, 33087, 6891, 1443]}
+
+
 def main():
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
@@ -58,6 +62,12 @@ def main():
             if precond == "amg":
                 msg.update(levels=info["levels"], distributed_levels=info["distributed_levels"],
                            level_rows=info["level_rows"], replicated_rows=info["replicated_rows"])
+            # the partitioned hierarchy is the numpy statement's (tests/amg_mirror.AMG(A, partitions=2,
+            # gather_below=...).rows): rank-local aggregation reproduces its level sizes exactly
+            want_rows = MIRROR_ROWS_2_RANKS.get((N, amg.get("gather_below"))) if world == 2 and amg.get("passes", 2) == 2 else None
+            if want_rows is not None:
+                msg["level_rows_match_numpy_statement"] = info["level_rows"][: len(want_rows)] == want_rows
+                ok &= msg["level_rows_match_numpy_statement"]
             if N in GOLD:
                 msg["rel_err_vs_reference"] = abs(r - GOLD[N]) / GOLD[N]
                 ok &= msg["rel_err_vs_reference"] < 1e-9

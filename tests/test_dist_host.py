@@ -80,3 +80,33 @@ def test_gloo_world_size_2():
     assert all(ok for _, ok, _, _ in res)
     total, ncomp = res[0][2], res[0][3]
     assert ncomp < total <= ncomp + 2 * 12 * 2     # boundary components are stamped on both ranks
+
+
+def test_share_upload_and_selection_preserve_stamping_order():
+    """Host path of the row-partitioned assembly (GridRunner.assemble_from_host): rank s uploads the
+    s-th contiguous share of the component table, selects per destination rank d the components
+    touching d's rows, and d concatenates what it receives in source-rank order.  Statement in numpy
+    of why that equals local_component_table(table, rows of d) -- same components, same (global
+    stamping) order -- for every rank count, including shares that select nothing."""
+    from nodal_b200 import dist as ndist
+    from nodal_b200 import generators as gen
+    for net in (gen.grid2d(17), gen.random_network(700, degree=6, seed=4), gen.random_network(700, degree=6, seed=5, locality=30)):
+        table = net.table()
+        m = len(table)
+        for world in (1, 2, 3, 8):
+            bounds = ndist.partition_rows(table.n, world)
+            received = {d: [] for d in range(world)}
+            for s in range(world):                                  # source ranks in rank order
+                lo, hi = m * s // world, m * (s + 1) // world
+                a, b = table.a[lo:hi], table.b[lo:hi]
+                for d in range(world):
+                    rb, re = int(bounds[d]), int(bounds[d + 1])
+                    touch = ((a >= rb) & (a < re)) | ((b >= rb) & (b < re))
+                    received[d].append(np.flatnonzero(touch) + lo)  # select keeps the share's order
+            for d in range(world):
+                got = np.concatenate(received[d])
+                want = ndist.local_component_table(table, int(bounds[d]), int(bounds[d + 1]))
+                assert len(got) == len(want)
+                assert np.array_equal(table.a[got], want.a) and np.array_equal(table.b[got], want.b)
+                assert np.array_equal(table.value[got], want.value)
+                assert np.all(np.diff(got) > 0)                     # global stamping order

@@ -51,14 +51,33 @@ KNIGHT_LIMIT = 4 / np.pi - 0.5       # infinite-grid knight's-move resistance
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
+def grid_rows(N):
+    """csv rows of the N x N 1-ohm grid of SURVEY.md section 8(d) (config C2 / C5a): for every site in row-major
+    order one resistor to the (x+1, y) and one to the (x, y+1) neighbour; probe node "1" at (N//2, N//2),
+    ground "g" a knight's move away at (N//2+2, N//2+1)."""
+    def name(x, y):
+        if (x, y) == (N // 2, N // 2):
+            return "1"
+        if (x, y) == (N // 2 + 2, N // 2 + 1):
+            return "g"
+        return f"n{x}_{y}"
+    rows = []
+    for x in range(N):
+        for y in range(N):
+            if x + 1 < N:
+                rows.append([f"r{len(rows)}", "R", "1.0", name(x, y), name(x + 1, y)])
+            if y + 1 < N:
+                rows.append([f"r{len(rows)}", "R", "1.0", name(x, y), name(x, y + 1)])
+    return rows
+
+
 def grid_csv(N):
     """The N x N grid netlist as the csv FILE the reference reads (written outside any timed region)."""
     import csv
     import tempfile
-    from oracle import mna_oracle as orc            # generator of the rows only
     fd, path = tempfile.mkstemp(prefix=f"grid{N}_", suffix=".csv")
     with os.fdopen(fd, "w", newline="") as fh:
-        csv.writer(fh).writerows(orc.grid2d_rows(N))
+        csv.writer(fh).writerows(grid_rows(N))
     return path
 
 
